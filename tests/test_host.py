@@ -1,0 +1,197 @@
+"""CPU-only: the drop-in boundary.  libzxc.so.4 loads, exports every symbol include/*.h
+declares (and the reference's 67), and the host-side logic (bounds, probes, dict container,
+SEK parsing, frame planning, header-level rejects) matches the reference.  No compute calls."""
+import ctypes as C
+import glob
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import zxc_corpus as zc
+import zxc_ctypes as z
+from conftest import has_cuda
+
+ROOT = z.ROOT
+G = os.path.join(ROOT, "tests", "golden")
+
+
+def declared_symbols():
+    names = set()
+    for h in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        src = open(h).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        for m in re.finditer(r"ZXC_EXPORT\s+[^;(]*?\b(zxc_\w+)\s*\(", src):
+            names.add(m.group(1))
+    return names
+
+
+def exported(path):
+    out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True).stdout
+    return {l.split()[-1] for l in out.splitlines() if l.strip()}
+
+
+def test_library_loads_and_exports_declared_symbols(prod):
+    decl = declared_symbols()
+    exp = exported(z.PRODUCT_SO)
+    assert len(decl) >= 67
+    assert decl <= exp, sorted(decl - exp)
+    for n in decl:
+        getattr(prod.lib, n)  # resolvable through the loader
+    so = subprocess.run(["readelf", "-d", z.PRODUCT_SO], capture_output=True, text=True).stdout
+    assert "libzxc.so.4" in so  # SONAME of the reference (CMakeLists.txt:64-71)
+
+
+def test_exports_superset_of_reference(prod, ref):
+    refsyms = {s for s in exported(z.REF_SO) if s.startswith("zxc_")}
+    assert len(refsyms) == 67
+    assert refsyms <= exported(z.PRODUCT_SO)
+
+
+def test_info_and_bounds_match_reference(prod, ref):
+    assert prod.lib.zxc_version_string() == ref.lib.zxc_version_string() == b"0.13.3"
+    for f in ("zxc_min_level", "zxc_max_level", "zxc_default_level"):
+        assert getattr(prod.lib, f)() == getattr(ref.lib, f)()
+    for lib in (prod.lib, ref.lib):
+        lib.zxc_compress_opts_size.restype = C.c_size_t
+        lib.zxc_decompress_opts_size.restype = C.c_size_t
+        lib.zxc_seek_table_size.restype = C.c_size_t
+        lib.zxc_seek_table_size.argtypes = [C.c_uint32]
+    assert prod.lib.zxc_compress_opts_size() == ref.lib.zxc_compress_opts_size() == C.sizeof(z.CompressOpts)
+    assert prod.lib.zxc_decompress_opts_size() == ref.lib.zxc_decompress_opts_size() == C.sizeof(z.DecompressOpts)
+    for n in (0, 1, 4095, 4096, 4097, 65536, 1 << 20, (1 << 21) + 1, 1 << 33):
+        assert prod.lib.zxc_compress_bound(n) == ref.lib.zxc_compress_bound(n)
+        assert prod.lib.zxc_compress_block_bound(n) == ref.lib.zxc_compress_block_bound(n)
+        assert prod.lib.zxc_decompress_block_bound(n) == ref.lib.zxc_decompress_block_bound(n)
+    for n in (0, 1, 1000, 1 << 20):
+        assert prod.lib.zxc_seek_table_size(n) == ref.lib.zxc_seek_table_size(n)
+    for code in list(range(-19, 1)):
+        assert prod.lib.zxc_error_name(code) == ref.lib.zxc_error_name(code)
+
+
+def test_probes_and_dict_container_match_reference(prod, ref):
+    rng = np.random.default_rng(1)
+    for p in sorted(glob.glob(os.path.join(G, "valid", "*.zxc")) + glob.glob(os.path.join(G, "invalid", "*.zxc"))
+                    + glob.glob(os.path.join(G, "format", "*.zxc"))):
+        b = open(p, "rb").read()
+        if not b:
+            continue
+        assert prod.lib.zxc_get_decompressed_size(b, len(b)) == ref.lib.zxc_get_decompressed_size(b, len(b)), p
+        assert prod.lib.zxc_get_dict_id(b, len(b)) == ref.lib.zxc_get_dict_id(b, len(b)), p
+    for n in (1, 5, 16, 17, 100, 113, 1000, 65535):
+        d = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        huf = rng.integers(0, 12, 128, dtype=np.uint8).tobytes()
+        assert prod.lib.zxc_dict_id(d, n, None) == ref.lib.zxc_dict_id(d, n, None)
+        assert prod.lib.zxc_dict_id(d, n, huf) == ref.lib.zxc_dict_id(d, n, huf)
+        for lib in (prod.lib, ref.lib):
+            lib.zxc_dict_save.restype = C.c_int64
+            lib.zxc_dict_save.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t]
+        a = np.zeros(n + 200, np.uint8)
+        bb = np.zeros(n + 200, np.uint8)
+        ra = prod.lib.zxc_dict_save(d, n, huf, a.ctypes.data, a.size)
+        rb = ref.lib.zxc_dict_save(d, n, huf, bb.ctypes.data, bb.size)
+        assert ra == rb == n + 144 and np.array_equal(a, bb)
+        rc, content, h2, did = prod.dict_load(a[:ra])
+        assert rc == 0 and content == d and h2 == huf and did == ref.lib.zxc_dict_id(d, n, huf)
+    for p in glob.glob(os.path.join(G, "valid", "*.zxd")):
+        b = open(p, "rb").read()
+        assert prod.dict_load(b) == ref.dict_load(b)
+        prod.lib.zxc_dict_get_id.restype = C.c_uint32
+        ref.lib.zxc_dict_get_id.restype = C.c_uint32
+        assert prod.lib.zxc_dict_get_id(b, len(b)) == ref.lib.zxc_dict_get_id(b, len(b))
+
+
+def test_seek_table_and_plan(prod, ref, orc):
+    data = zc.silesia_shaped(1 << 20, seed=4)[:700001]
+    for cks in (0, 1):
+        frame = ref.compress(data, level=3, block_size=65536, checksum=cks, seekable=1)
+        fb = frame.tobytes()
+        hp = prod.lib.zxc_seekable_open(fb, len(fb))
+        hr = ref.lib.zxc_seekable_open(fb, len(fb))
+        assert hp and hr
+        nb = ref.lib.zxc_seekable_get_num_blocks(hr)
+        assert prod.lib.zxc_seekable_get_num_blocks(hp) == nb == 11
+        assert prod.lib.zxc_seekable_get_decompressed_size(hp) == ref.lib.zxc_seekable_get_decompressed_size(hr)
+        for i in range(nb + 2):
+            assert prod.lib.zxc_seekable_get_block_comp_size(hp, i) == ref.lib.zxc_seekable_get_block_comp_size(hr, i)
+            assert prod.lib.zxc_seekable_get_block_decomp_size(hp, i) == ref.lib.zxc_seekable_get_block_decomp_size(hr, i)
+        # job table from the sequential walk agrees with the SEK table
+        class Job(C.Structure):
+            _fields_ = [("src_off", C.c_uint64), ("dst_off", C.c_uint64), ("src_len", C.c_uint32), ("dst_cap", C.c_uint32)]
+        class Info(C.Structure):
+            _fields_ = [("decoded_size", C.c_uint64), ("block_size", C.c_uint32), ("n_blocks", C.c_uint32),
+                        ("dict_id", C.c_uint32), ("has_checksum", C.c_int), ("seekable", C.c_int), ("global_hash", C.c_uint32)]
+        prod.lib.zxc_b200_plan_frame.restype = C.c_int64
+        prod.lib.zxc_b200_plan_frame.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+        jobs = (Job * nb)()
+        info = Info()
+        assert prod.lib.zxc_b200_plan_frame(fb, len(fb), jobs, nb, C.byref(info)) == nb
+        assert info.decoded_size == data.size and info.block_size == 65536 and info.seekable == 1
+        assert info.has_checksum == cks
+        off = 16
+        for i in range(nb):
+            assert jobs[i].src_off == off and jobs[i].src_len == ref.lib.zxc_seekable_get_block_comp_size(hr, i)
+            assert jobs[i].dst_off == i * 65536
+            assert jobs[i].dst_cap == ref.lib.zxc_seekable_get_block_decomp_size(hr, i)
+            off += jobs[i].src_len
+        prod.lib.zxc_seekable_free(hp)
+        ref.lib.zxc_seekable_free(hr)
+        # not-seekable / damaged SEK -> NULL handle in both
+        plain = ref.compress(data, level=3, block_size=65536, checksum=cks, seekable=0).tobytes()
+        assert not prod.lib.zxc_seekable_open(plain, len(plain)) and not ref.lib.zxc_seekable_open(plain, len(plain))
+        bad = bytearray(fb)
+        bad[-20] ^= 0x55
+        bad = bytes(bad)
+        assert bool(prod.lib.zxc_seekable_open(bad, len(bad))) == bool(ref.lib.zxc_seekable_open(bad, len(bad)))
+
+
+def test_write_seek_table_matches_reference(prod, ref):
+    sizes = np.array([22, 4000, 70000, 8, 123456], dtype="<u4")
+    for lib in (prod.lib, ref.lib):
+        lib.zxc_write_seek_table.restype = C.c_int64
+        lib.zxc_write_seek_table.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32]
+    a = np.zeros(64, np.uint8)
+    b = np.zeros(64, np.uint8)
+    assert prod.lib.zxc_write_seek_table(a.ctypes.data, 64, sizes.ctypes.data, 5) == 28
+    assert ref.lib.zxc_write_seek_table(b.ctypes.data, 64, sizes.ctypes.data, 5) == 28
+    assert np.array_equal(a, b)
+    assert prod.lib.zxc_write_seek_table(a.ctypes.data, 27, sizes.ctypes.data, 5) == -2
+
+
+HOST_LEVEL = ["zero_length", "too_short_4bytes", "truncated_header_only", "all_0xff_garbage", "bad_magic",
+              "magic_then_zeros", "bad_version", "bad_header_crc", "bad_checksum_algo", "bad_block_size_field"]
+
+
+@pytest.mark.parametrize("name", HOST_LEVEL)
+def test_header_level_rejects_need_no_device(prod, name):
+    exp = json.load(open(os.path.join(G, "invalid", "expected.json")))[name]
+    frame = open(os.path.join(G, "invalid", name + ".zxc"), "rb").read()
+    out = np.zeros(1 << 16, np.uint8)
+    o = z.DecompressOpts(checksum_enabled=1)
+    r = prod.lib.zxc_decompress(frame if frame else b"\0", len(frame), out.ctypes.data, out.size, C.byref(o))
+    assert r == exp, z.ERR.get(r)
+
+
+def test_argument_checks(prod):
+    out = np.zeros(64, np.uint8)
+    assert prod.lib.zxc_decompress(None, 100, out.ctypes.data, 64, None) == -12
+    assert prod.lib.zxc_decompress(b"x" * 10, 10, out.ctypes.data, 64, None) == -3
+    empty = open(os.path.join(G, "valid", "empty.zxc"), "rb").read()
+    assert prod.lib.zxc_decompress(empty, len(empty), None, 0, None) == 0
+    one = open(os.path.join(G, "valid", "one_byte.zxc"), "rb").read()
+    assert prod.lib.zxc_decompress(one, len(one), None, 0, None) == -2
+    assert prod.lib.zxc_compress(b"abc", 3, None, 0, None) == -12
+    o = z.CompressOpts(block_size=12345)
+    assert prod.lib.zxc_compress(b"abc", 3, out.ctypes.data, 64, C.byref(o)) == -14
+
+
+@pytest.mark.skipif(has_cuda(), reason="only meaningful without a GPU")
+def test_no_device_fails_loudly(prod):
+    """There is no CPU codec behind the API: a valid frame on a GPU-less host is an error."""
+    frame = open(os.path.join(G, "valid", "text_64k_level3.zxc"), "rb").read()
+    r, _ = prod.decompress(frame, 65536)
+    assert r == -100 and prod.lib.zxc_error_name(r) == b"ZXC_B200_ERROR_NO_DEVICE"
+    assert prod.lib.zxc_b200_device_count() == 0

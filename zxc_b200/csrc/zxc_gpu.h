@@ -1,0 +1,52 @@
+/*
+ * zxc_gpu.h -- internal C interface between the host C code (zxc_api.c,
+ * zxc_frame.c) and the CUDA translation unit (zxc_gpu.cu).  Plain C types only.
+ */
+#ifndef ZXC_B200_GPU_H
+#define ZXC_B200_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "zxc_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* A device context: one CUDA stream plus growable device / pinned buffers that
+ * survive between calls.  The buffer API is stateless and thread-safe in the
+ * reference (docs/API.md:1530-1538), so contexts come from a mutex-guarded
+ * free list instead of a global singleton stream. */
+typedef struct zxg_ctx zxg_ctx;
+
+/* ZXC_OK, or ZXC_B200_ERROR_NO_DEVICE (message printed once to stderr). */
+int zxg_init(void);
+zxg_ctx* zxg_acquire(void);
+void zxg_release(zxg_ctx* c);
+void zxg_destroy(zxg_ctx* c); /* for contexts owned by a zxc_dctx / zxc_seekable */
+zxg_ctx* zxg_create(void);
+
+/* Named device buffers of a context, grown on demand (never shrunk). */
+enum { ZXG_BUF_IN = 0, ZXG_BUF_OUT, ZXG_BUF_JOBS, ZXG_BUF_STATUS, ZXG_BUF_DICT, ZXG_BUF_SCRATCH,
+       ZXG_BUF_AUX, ZXG_BUF_COUNT };
+void* zxg_buffer(zxg_ctx* c, int which, size_t bytes); /* NULL on allocation failure */
+
+/* Host <-> device copies on the context's stream.  Pageable host memory is
+ * staged through the context's pinned bounce buffers in chunks so the copy and
+ * the host memcpy overlap. */
+int zxg_h2d(zxg_ctx* c, void* d_dst, const void* h_src, size_t bytes);
+int zxg_d2h(zxg_ctx* c, void* h_dst, const void* d_src, size_t bytes);
+int zxg_sync(zxg_ctx* c);
+void* zxg_stream(zxg_ctx* c);
+
+/* Whole decode step for host-resident input: upload jobs, launch, fetch statuses.
+ * h_status receives n_jobs entries. */
+int zxg_decode_jobs(zxg_ctx* c, const void* d_src, void* d_dst, const zxc_b200_job_t* h_jobs,
+                    uint32_t n_jobs, int32_t* h_status, const void* h_dict, uint32_t dict_size,
+                    const void* h_dict_huf, uint32_t block_size, int verify_checksums);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
