@@ -1,0 +1,617 @@
+/*
+ * zxc_decode.cuh -- sm_100a block-decode kernels (device code only).
+ *
+ * One warp per independent block; lane = sequence,
+ * 32 sequences per batch:
+ *   1. token / offset unpack               (GLO zxc_decompress.c:626-694, GHI :701-727)
+ *   2. escape resolution over the extras   (varint, :51-88): the batch's k escapes are walked
+ *      once, warp-uniformly; each lane keeps the value(s) whose ordinal (ballot + popc) is its own
+ *   3. warp prefix sums -> literal source offset and output offset per lane
+ *   4. bounds / offset validation; first failing lane == first failing sequence
+ *   5. literal copies (independent), then match copies in dependency rounds: a match is ready
+ *      when its source ends below the lowest pending match destination
+ *   6. the output is staged in a per-warp shared-memory ring and leaves the SM as coalesced
+ *      16-byte stores (512 B per warp instruction); match sources come from the ring when they
+ *      are recent and from global memory (L2) once flushed.
+ * Overlapping matches (off < ml) use the period-`off` index instead of the reference's shuffle
+ * tables (:197-413).  Output is written exactly (no wild-copy overshoot): none of the
+ * reference's PAD / TAIL_PAD slack is needed on the destination; the wire-level 32-byte
+ * literal slack rule stays normative (:1003).
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "zxc_b200.h"
+#include "zxc_error.h"
+
+typedef uint8_t u8;
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef int32_t i32;
+
+#define FULL 0xFFFFFFFFu
+#define WARPS_PER_CTA 4
+#define CTA_THREADS (WARPS_PER_CTA * 32)
+#define RING_BYTES 8192u          /* per-warp output ring (power of two, multiple of 512) */
+#define RING_LIMIT (RING_BYTES - 576u) /* largest output span one batch may add */
+#define DECODE_SMEM_BYTES (WARPS_PER_CTA * RING_BYTES)
+#define CTAS_PER_SM 7u            /* 227 KB / 32 KB of ring per CTA */
+
+#define BT_RAW 0
+#define BT_GLO 1
+#define BT_GHI 2
+#define BT_EOF 255
+
+#define FLAG_VERIFY 1u
+
+struct DecodeParams {
+    const u8* src;
+    u8* dst;
+    const zxc_b200_job_t* jobs;
+    i32* status;
+    const u8* dict;
+    const u8* dict_huf;
+    u8* scratch;
+    unsigned long long* counter;
+    u32 n_jobs;
+    u32 dict_size;
+    u32 scratch_stride;
+    u32 flags;
+};
+
+/* ------------------------------------------------------------------------- */
+/* small device helpers                                                      */
+/* ------------------------------------------------------------------------- */
+__device__ __forceinline__ u32 ld16(const u8* p) { return (u32)p[0] | ((u32)p[1] << 8); }
+__device__ __forceinline__ u32 ld32(const u8* p) {
+    return (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24);
+}
+__device__ __forceinline__ u64 ld64(const u8* p) { return (u64)ld32(p) | ((u64)ld32(p + 4) << 32); }
+
+__device__ __forceinline__ u32 warp_incl_scan(u32 v, u32 lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u32 t = __shfl_up_sync(FULL, v, d);
+        if (lane >= (u32)d) v += t;
+    }
+    return v;
+}
+
+/* warp-wide byte copy, global -> global, non-overlapping */
+__device__ __forceinline__ void warp_copy(u8* d, const u8* s, u32 n, u32 lane) {
+    u32 k = lane;
+    for (; k + 96 < n; k += 128) {
+        const u8 a = s[k], b = s[k + 32], c = s[k + 64], e = s[k + 96];
+        d[k] = a;
+        d[k + 32] = b;
+        d[k + 64] = c;
+        d[k + 96] = e;
+    }
+    for (; k < n; k += 32) d[k] = s[k];
+}
+
+/* prefix varint with the reference's exact failure behaviour (zxc_decompress.c:51-88):
+ * value 0 and the cursor jams to `end`, except at/after end where it stays. */
+__device__ __forceinline__ u32 read_varint(const u8* e, u32& pos, u32 end) {
+    if (pos >= end) return 0;
+    const u32 b0 = e[pos];
+    if (b0 < 0x80) {
+        pos += 1;
+        return b0;
+    }
+    if (b0 < 0xC0) {
+        if (pos + 1 >= end) {
+            pos = end;
+            return 0;
+        }
+        const u32 v = (b0 & 0x3F) | ((u32)e[pos + 1] << 6);
+        pos += 2;
+        return v;
+    }
+    if (b0 < 0xE0) {
+        if (pos + 2 >= end) {
+            pos = end;
+            return 0;
+        }
+        const u32 v = (b0 & 0x1F) | ((u32)e[pos + 1] << 5) | ((u32)e[pos + 2] << 13);
+        pos += 3;
+        return v;
+    }
+    pos = end;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* rapidhash V3 folded to 32 bits, warp-cooperative (vendors/rapidhash.h).    */
+/* Lanes 0..6 own the seven stripe accumulators; the tail is warp-uniform.    */
+/* ------------------------------------------------------------------------- */
+__device__ __forceinline__ u64 mul_fold(u64 a, u64 b) { return (a * b) ^ __umul64hi(a, b); }
+
+__device__ u32 warp_checksum(const u8* p, u32 len, u32 lane) {
+    const u64 S0 = 0x2d358dccaa6c78a5ull, S1 = 0x8bb84b93962eacc9ull, S2 = 0x4b33a62ed433d4a3ull,
+              S3 = 0x4d5a2da51de1aa47ull, S4 = 0xa0761d6478bd642full, S5 = 0xe7037ed1a0b428dbull,
+              S6 = 0x90ed1765281c388cull, S7 = 0xaaaaaaaaaaaaaaaaull;
+    u64 seed = 0;
+    seed ^= mul_fold(seed ^ S2, S1);
+    u64 a = 0, b = 0;
+    u32 rem = len;
+    if (len <= 16) {
+        if (len >= 8) {
+            seed ^= len;
+            a = ld64(p);
+            b = ld64(p + len - 8);
+        } else if (len >= 4) {
+            seed ^= len;
+            a = ld32(p);
+            b = ld32(p + len - 4);
+        } else if (len > 0) {
+            a = ((u64)p[0] << 45) | p[len - 1];
+            b = p[len >> 1];
+        }
+    } else {
+        if (len > 112) {
+            const u64 sk = lane == 0 ? S0 : lane == 1 ? S1 : lane == 2 ? S2 : lane == 3 ? S3
+                         : lane == 4 ? S4 : lane == 5 ? S5 : S6;
+            u64 acc = seed;
+            const u32 stripes = (len - 1) / 112; /* while (rem > 112) */
+            if (lane < 7) {
+                const u8* q = p + 16 * lane;
+                for (u32 s = 0; s < stripes; s++, q += 112) acc = mul_fold(ld64(q) ^ sk, ld64(q + 8) ^ acc);
+            }
+            u64 x = (lane < 7) ? acc : 0;
+#pragma unroll
+            for (int d = 4; d >= 1; d >>= 1) x ^= __shfl_xor_sync(FULL, x, d);
+            seed = __shfl_sync(FULL, x, 0); /* lanes 0..7 xor-reduced: accumulators 0..6 */
+            p += (size_t)stripes * 112;
+            rem -= stripes * 112;
+        }
+        const u64 ts[6] = {S2, S2, S1, S1, S2, S1};
+#pragma unroll
+        for (u32 k = 0; k < 6; k++)
+            if (rem > 16u * (k + 1)) seed = mul_fold(ld64(p + 16 * k) ^ ts[k], ld64(p + 16 * k + 8) ^ seed);
+        a = ld64(p + rem - 16) ^ rem;
+        b = ld64(p + rem - 8);
+    }
+    a ^= S1;
+    b ^= seed;
+    const u64 lo = a * b, hi = __umul64hi(a, b);
+    const u64 h = mul_fold(lo ^ S7, hi ^ S1 ^ rem);
+    return (u32)(h ^ (h >> 32));
+}
+
+/* ------------------------------------------------------------------------- */
+/* RLE literal section -> scratch (zxc_decompress.c:906-978)                  */
+/* ------------------------------------------------------------------------- */
+__device__ int rle_expand(const u8* r, u32 rsz, u8* w, u32 wsz, u32 lane) {
+    u32 rp = 0, wp = 0;
+    while (rp < rsz && wp < wsz) {
+        const u32 t = r[rp++];
+        if (!(t & 0x80)) {
+            const u32 len = t + 1;
+            if (wsz - wp < len || rsz - rp < len) return ZXC_ERROR_CORRUPT_DATA;
+            for (u32 k = lane; k < len; k += 32) w[wp + k] = r[rp + k];
+            wp += len;
+            rp += len;
+        } else {
+            const u32 len = (t & 0x7F) + 4;
+            if (wsz - wp < len || rp >= rsz) return ZXC_ERROR_CORRUPT_DATA;
+            const u8 v = r[rp++];
+            for (u32 k = lane; k < len; k += 32) w[wp + k] = v;
+            wp += len;
+        }
+    }
+    return wp == wsz ? ZXC_OK : ZXC_ERROR_CORRUPT_DATA;
+}
+
+/* ------------------------------------------------------------------------- */
+/* section layout of a GLO / GHI payload (zxc_common.c:773-832 +              */
+/* zxc_decompress.c:859-1023, :1241-1269), checks in the reference's order    */
+/* ------------------------------------------------------------------------- */
+struct Sections {
+    const u8* lit;
+    const u8* tok;  /* GLO tokens or GHI sequence words */
+    const u8* offs; /* GLO offsets */
+    const u8* ext;
+    u32 ext_end;
+    u32 n_lit_avail;
+    u32 n_seq;
+    u32 enc_off;
+};
+
+__device__ int parse_sections(const u8* pay, u32 comp, bool ghi, u32 cap, const u8* dict_huf, u8* scratch,
+                              u32 scratch_cap, u32 lane, Sections& S) {
+    if (comp < 12) return ZXC_ERROR_BAD_HEADER;
+    const u32 n_seq = ld32(pay), n_lit = ld32(pay + 4);
+    const u32 enc_lit = pay[8], enc_tok = pay[9], enc_off = pay[11];
+    S.n_seq = n_seq;
+    S.enc_off = enc_off;
+    S.offs = 0;
+    if (!ghi) {
+        const u32 desc = (enc_lit != 0 ? 4u : 0u) + (enc_tok == 2 ? 4u : 0u);
+        if (comp < 12 + desc) return ZXC_ERROR_BAD_HEADER;
+        u32 lit_comp = n_lit, tok_comp = n_seq;
+        const u8* dp = pay + 12;
+        if (enc_lit != 0) {
+            lit_comp = ld32(dp);
+            dp += 4;
+        }
+        if (enc_tok == 2) tok_comp = ld32(dp);
+        if (enc_off > 1) return ZXC_ERROR_CORRUPT_DATA;
+        const u8* p_data = pay + 12 + desc;
+        const u32 avail = comp - 12 - desc;
+        if (enc_lit == 2 || enc_lit == 3) {
+            if (lit_comp > avail) return ZXC_ERROR_CORRUPT_DATA;
+            if (n_lit != 0) {
+                if (n_lit > cap) return ZXC_ERROR_DST_TOO_SMALL;
+                if (enc_lit == 3 && !dict_huf) return ZXC_ERROR_DICT_REQUIRED;
+                return ZXC_B200_ERROR_UNSUPPORTED; /* PivCo literal sections: SURVEY 8(f)-1 */
+            }
+            S.lit = p_data;
+            S.n_lit_avail = 0;
+        } else if (enc_lit == 1) {
+            if (n_lit > 0) {
+                if (n_lit > cap) return ZXC_ERROR_DST_TOO_SMALL;
+                if (n_lit > scratch_cap) return ZXC_ERROR_CORRUPT_DATA; /* lit_buffer_cap, :914 */
+                if (lit_comp > avail) return ZXC_ERROR_CORRUPT_DATA;
+                const int rc = rle_expand(p_data, lit_comp, scratch, n_lit, lane);
+                if (rc != ZXC_OK) return rc;
+                __syncwarp();
+                S.lit = scratch;
+                S.n_lit_avail = n_lit;
+            } else {
+                S.lit = p_data;
+                S.n_lit_avail = 0;
+            }
+        } else if (enc_lit == 0) {
+            S.lit = p_data;
+            S.n_lit_avail = lit_comp;
+        } else {
+            return ZXC_ERROR_CORRUPT_DATA;
+        }
+        const u64 sz_off = enc_off ? (u64)n_seq : (u64)n_seq * 2;
+        const u64 consumed = (u64)lit_comp + tok_comp + sz_off;
+        if (consumed > avail) return ZXC_ERROR_CORRUPT_DATA;
+        if (avail - lit_comp < 32) return ZXC_ERROR_CORRUPT_DATA;
+        if (enc_tok == 2) return ZXC_B200_ERROR_UNSUPPORTED; /* PivCo token sections: 8(f)-1 */
+        if (enc_tok != 0) return ZXC_ERROR_CORRUPT_DATA;
+        S.tok = p_data + lit_comp;
+        S.offs = S.tok + tok_comp;
+        S.ext = S.offs + (u32)sz_off;
+        S.ext_end = avail - (u32)consumed;
+    } else {
+        if (enc_lit != 0 || enc_tok != 0) return ZXC_ERROR_CORRUPT_DATA;
+        const u32 avail = comp - 12;
+        const u64 consumed = (u64)n_lit + (u64)n_seq * 4;
+        if (consumed > avail) return ZXC_ERROR_CORRUPT_DATA;
+        if (avail - n_lit < 32) return ZXC_ERROR_CORRUPT_DATA;
+        S.lit = pay + 12;
+        S.n_lit_avail = n_lit;
+        S.tok = S.lit + n_lit;
+        S.ext = S.tok + (size_t)n_seq * 4;
+        S.ext_end = avail - (u32)consumed;
+    }
+    return ZXC_OK;
+}
+
+/* ------------------------------------------------------------------------- */
+/* output window: ring (recent) + global (flushed) + dictionary (negative)    */
+/* ------------------------------------------------------------------------- */
+struct Window {
+    u8* ring;        /* this warp's RING_BYTES of shared memory, 16-byte aligned */
+    u8* out;         /* block output in global memory */
+    const u8* dict;  /* dictionary content or NULL */
+    u32 dict_size;
+    i32 near_lo;     /* positions >= near_lo are valid in the ring */
+};
+
+__device__ __forceinline__ u8 window_byte(const Window& w, i32 pos) {
+    if (pos >= w.near_lo) return w.ring[(u32)pos & (RING_BYTES - 1)];
+    return pos >= 0 ? w.out[pos] : w.dict[(i32)w.dict_size + pos];
+}
+__device__ __forceinline__ u8 far_byte(const Window& w, i32 pos) {
+    return pos >= 0 ? w.out[pos] : w.dict[(i32)w.dict_size + pos];
+}
+
+/* flush ring bytes [F, target) to global; 16-byte stores once (out + F) is 16-aligned */
+__device__ __forceinline__ void ring_flush(const Window& w, u32& F, u32 target, u32 lane, bool al16) {
+    const u32 mask = RING_BYTES - 1;
+    if (target <= F) return; /* after a giant sequence F may sit above the 512-byte floor of O */
+    if (al16) {
+        const u32 head_end = min(target, (F + 15u) & ~15u);
+        if (F < head_end) {
+            const u32 p = F + lane;
+            if (p < head_end) w.out[p] = w.ring[p & mask];
+            F = head_end;
+        }
+        while (target - F >= 512u) {
+            const uint4 v = *reinterpret_cast<const uint4*>(w.ring + ((F + 16u * lane) & mask));
+            *reinterpret_cast<uint4*>(w.out + F + 16u * lane) = v;
+            F += 512u;
+        }
+        const u32 units = (target - F) >> 4;
+        if (lane < units) {
+            const uint4 v = *reinterpret_cast<const uint4*>(w.ring + ((F + 16u * lane) & mask));
+            *reinterpret_cast<uint4*>(w.out + F + 16u * lane) = v;
+        }
+        F += units << 4;
+    }
+    for (u32 p = F + lane; p < target; p += 32) w.out[p] = w.ring[p & mask];
+    F = target;
+}
+
+/* whole-warp match copy of n bytes into the ring at d from distance off */
+__device__ __forceinline__ void warp_match_to_ring(const Window& w, u32 d, u32 off, u32 n, u32 lane) {
+    const u32 mask = RING_BYTES - 1;
+    if (off >= 32) {
+        /* chunk c only reads bytes below its own start: earlier chunks are complete */
+        for (u32 c = 0; c < n; c += 32) {
+            const u32 k = c + lane;
+            if (k < n) w.ring[(d + k) & mask] = window_byte(w, (i32)(d + k) - (i32)off);
+            __syncwarp();
+        }
+    } else {
+        /* period-`off` replication of the complete window [d-off, d) */
+        for (u32 k = lane; k < n; k += 32)
+            w.ring[(d + k) & mask] = window_byte(w, (i32)d - (i32)off + (i32)(k % off));
+    }
+}
+
+/* whole-warp match copy global -> global (giant sequences that bypass the ring) */
+__device__ __forceinline__ void warp_match_global(const Window& w, u32 d, u32 off, u32 n, u32 lane) {
+    if (off >= 32) {
+        for (u32 c = 0; c < n; c += 32) {
+            const u32 k = c + lane;
+            if (k < n) w.out[d + k] = far_byte(w, (i32)(d + k) - (i32)off);
+            __syncwarp();
+        }
+    } else {
+        for (u32 k = lane; k < n; k += 32) w.out[d + k] = far_byte(w, (i32)d - (i32)off + (i32)(k % off));
+    }
+}
+
+#define LIT_SHORT 16u
+#define MATCH_SHORT 32u
+
+/* ------------------------------------------------------------------------- */
+/* GLO / GHI block body.  Returns decoded bytes or a negative zxc_error_t.    */
+/* ------------------------------------------------------------------------- */
+__device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 cap, const u8* dict,
+                               u32 dict_size, const u8* dict_huf, u8* scratch, u32 scratch_cap, u8* ring,
+                               u32 lane) {
+    Sections S;
+    const int prc = parse_sections(pay, comp, ghi, cap, dict_huf, scratch, scratch_cap, lane, S);
+    if (prc != ZXC_OK) return prc;
+    const u8* lit = S.lit;
+    const u8* tok = S.tok;
+    const u8* offs = S.offs;
+    const u8* ext = S.ext;
+    const u32 ext_end = S.ext_end, n_lit_avail = S.n_lit_avail, n_seq = S.n_seq, enc_off = S.enc_off;
+
+    const u32 mask = RING_BYTES - 1;
+    const u32 esc = ghi ? 255u : 15u;
+    const u32 lt_mask = (1u << lane) - 1u;
+    const bool al16 = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+    Window w;
+    w.ring = ring;
+    w.out = out;
+    w.dict = dict;
+    w.dict_size = dict_size;
+    w.near_lo = 0;
+    u32 O = 0, L = 0, F = 0, epos = 0, ring_lo = 0;
+
+    u32 base = 0;
+    while (base < n_seq) {
+        const u32 i = base + lane;
+        const bool valid = i < n_seq;
+        u32 ll = 0, ml = 0, off = 1;
+        if (valid) {
+            if (!ghi) {
+                const u32 t = tok[i];
+                ll = t >> 4;
+                ml = t & 15;
+                off = (enc_off ? (u32)offs[i] : ld16(offs + 2 * (size_t)i)) + 1;
+            } else {
+                const u32 wd = ld32(tok + 4 * (size_t)i);
+                ll = wd >> 24;
+                ml = (wd >> 16) & 0xFF;
+                off = (wd & 0xFFFF) + 1;
+            }
+        }
+        /* ---- escapes: one uniform walk over the batch's varints ---- */
+        const bool e_ll = valid && ll == esc, e_ml = valid && ml == esc;
+        const u32 m_ll = __ballot_sync(FULL, e_ll), m_ml = __ballot_sync(FULL, e_ml);
+        u32 step_lo = 0, step_hi = 0, k_esc = 0, epos_end = epos;
+        if (m_ll | m_ml) {
+            const u32 ord_ll = __popc(m_ll & lt_mask) + __popc(m_ml & lt_mask);
+            const u32 ord_ml = ord_ll + (e_ll ? 1u : 0u);
+            k_esc = __popc(m_ll) + __popc(m_ml);
+            for (u32 s = 0; s < k_esc; s++) {
+                if (s == lane) step_lo = epos_end;
+                if (s == lane + 32) step_hi = epos_end;
+                const u32 v = read_varint(ext, epos_end, ext_end);
+                if (e_ll && s == ord_ll) ll += v;
+                if (e_ml && s == ord_ml) ml += v;
+            }
+        }
+        if (valid) ml += 5;
+        const u32 tot = ll + ml;
+        const u32 s_ll = warp_incl_scan(ll, lane);
+        const u32 s_tot = warp_incl_scan(tot, lane);
+
+        /* ---- how many leading sequences fit the ring this round ---- */
+        const u32 nvalid = min(32u, n_seq - base);
+        const u32 m = __popc(__ballot_sync(FULL, valid && s_tot <= RING_LIMIT));
+        const u32 lit_start = L + s_ll - ll;
+        const u32 out_start = O + s_tot - tot;
+        const u32 mdst = out_start + ll;
+
+        if (m == 0) {
+            /* ---- giant sequence (lane 0): bypass the ring, global -> global ---- */
+            const u32 g_ll = __shfl_sync(FULL, ll, 0), g_ml = __shfl_sync(FULL, ml, 0),
+                      g_off = __shfl_sync(FULL, off, 0);
+            if (L + g_ll > n_lit_avail || (u64)O + g_ll + g_ml > cap) return ZXC_ERROR_OVERFLOW;
+            if (O + g_ll + dict_size < g_off) return ZXC_ERROR_BAD_OFFSET;
+            __syncwarp();
+            ring_flush(w, F, O, lane, al16);
+            __syncwarp();
+            warp_copy(out + O, lit + L, g_ll, lane);
+            __syncwarp();
+            warp_match_global(w, O + g_ll, g_off, g_ml, lane);
+            __syncwarp();
+            O += g_ll + g_ml;
+            L += g_ll;
+            F = O;
+            /* re-seed the ring with the last 64 bytes so short sources that straddle O resolve */
+            ring_lo = O >= 64 ? O - 64 : 0;
+            for (u32 p = ring_lo + lane; p < O; p += 32) ring[p & mask] = out[p];
+            __syncwarp();
+            const u32 q = ((m_ll & 1u) ? 1u : 0u) + ((m_ml & 1u) ? 1u : 0u);
+            epos = (q == k_esc) ? epos_end : __shfl_sync(FULL, step_lo, q);
+            base += 1;
+            continue;
+        }
+
+        const bool act = lane < m;
+        const bool ovf = act && (lit_start + ll > n_lit_avail || out_start + tot > cap);
+        const bool bad = act && (mdst + dict_size < off);
+        const u32 m_err = __ballot_sync(FULL, ovf || bad);
+        if (m_err) {
+            const int code = ovf ? ZXC_ERROR_OVERFLOW : ZXC_ERROR_BAD_OFFSET;
+            return __shfl_sync(FULL, code, __ffs(m_err) - 1);
+        }
+        const u32 T = __shfl_sync(FULL, s_tot, m - 1), TL = __shfl_sync(FULL, s_ll, m - 1);
+        {
+            const i32 a = (i32)(O + T) - (i32)RING_BYTES + 32;
+            w.near_lo = a > (i32)ring_lo ? a : (i32)ring_lo;
+        }
+
+        /* ---- literals: independent of every match ---- */
+        if (act && ll <= LIT_SHORT) {
+            for (u32 k = 0; k < ll; k++) ring[(out_start + k) & mask] = lit[lit_start + k];
+        }
+        u32 m_long = __ballot_sync(FULL, act && ll > LIT_SHORT);
+        while (m_long) {
+            const int j = __ffs(m_long) - 1;
+            m_long &= m_long - 1;
+            const u32 d = __shfl_sync(FULL, out_start, j), s = __shfl_sync(FULL, lit_start, j),
+                      n = __shfl_sync(FULL, ll, j);
+            for (u32 k = lane; k < n; k += 32) ring[(d + k) & mask] = lit[s + k];
+        }
+        __syncwarp();
+
+        /* ---- matches: dependency rounds ---- */
+        u32 pending = __ballot_sync(FULL, act);
+        const i32 src_lo = (i32)mdst - (i32)off;
+        const i32 src_end = min((i32)mdst, src_lo + (i32)ml);
+        while (pending) {
+            const int first = __ffs(pending) - 1;
+            const i32 W = (i32)__shfl_sync(FULL, mdst, first);
+            const bool ready = ((pending >> lane) & 1u) && ((int)lane == first || src_end <= W);
+            if (ready && ml <= MATCH_SHORT) {
+                for (u32 k = 0; k < ml; k++) ring[(mdst + k) & mask] = window_byte(w, src_lo + (i32)k);
+            }
+            u32 m_lm = __ballot_sync(FULL, ready && ml > MATCH_SHORT);
+            while (m_lm) {
+                const int j = __ffs(m_lm) - 1;
+                m_lm &= m_lm - 1;
+                warp_match_to_ring(w, __shfl_sync(FULL, mdst, j), __shfl_sync(FULL, off, j),
+                                   __shfl_sync(FULL, ml, j), lane);
+            }
+            pending &= ~__ballot_sync(FULL, ready);
+            __syncwarp();
+        }
+
+        O += T;
+        L += TL;
+        ring_flush(w, F, O & ~511u, lane, al16);
+        __syncwarp();
+
+        if (m < nvalid) {
+            const u32 below = (1u << m) - 1u;
+            const u32 q = __popc(m_ll & below) + __popc(m_ml & below);
+            epos = (q == k_esc) ? epos_end : (q < 32 ? __shfl_sync(FULL, step_lo, q) : __shfl_sync(FULL, step_hi, q - 32));
+            base += m;
+        } else {
+            epos = epos_end;
+            base += 32;
+        }
+    }
+
+    /* trailing literals (zxc_decompress.c:1198-1206) */
+    const u32 rem = n_lit_avail - L;
+    if (rem > cap - O) return ZXC_ERROR_OVERFLOW;
+    ring_flush(w, F, O, lane, al16);
+    __syncwarp();
+    warp_copy(out + O, lit + L, rem, lane);
+    return (int)(O + rem);
+}
+
+/* zxc_decompress_chunk_wrapper_body (zxc_decompress.c:1646-1695) for one job */
+__device__ int decode_job(const DecodeParams& P, const zxc_b200_job_t& job, u8* scratch, u8* ring, u32 lane) {
+    const u8* blk = P.src + job.src_off;
+    u8* out = P.dst + job.dst_off;
+    if (job.src_len < 8) return ZXC_ERROR_SRC_TOO_SMALL;
+    const u32 type = blk[0];
+    const u32 comp = ld32(blk + 3);
+    const bool verify = (P.flags & FLAG_VERIFY) != 0;
+    if ((u64)job.src_len < 8ull + comp + (verify ? 4u : 0u)) return ZXC_ERROR_SRC_TOO_SMALL;
+    const u8* data = blk + 8;
+    if (verify) {
+        if (ld32(data + comp) != warp_checksum(data, comp, lane)) return ZXC_ERROR_BAD_CHECKSUM;
+    }
+    switch (type) {
+        case BT_GLO:
+        case BT_GHI:
+            return decode_lz_block(data, comp, type == BT_GHI, out, job.dst_cap, P.dict, P.dict_size,
+                                   P.dict_huf, scratch, P.scratch_stride, ring, lane);
+        case BT_RAW:
+            if (comp > job.dst_cap) return ZXC_ERROR_DST_TOO_SMALL;
+            warp_copy(out, data, comp, lane);
+            return (int)comp;
+        case BT_EOF:
+            return ZXC_ERROR_CORRUPT_DATA;
+        default:
+            return ZXC_ERROR_BAD_BLOCK_TYPE;
+    }
+}
+
+__global__ void __launch_bounds__(CTA_THREADS) zxc_decode_kernel(const DecodeParams P) {
+    extern __shared__ __align__(16) u8 smem[];
+    const u32 lane = threadIdx.x & 31;
+    const u32 wic = threadIdx.x >> 5;
+    const u32 gwarp = blockIdx.x * WARPS_PER_CTA + wic;
+    u8* scratch = P.scratch + (size_t)gwarp * P.scratch_stride;
+    u8* ring = smem + (size_t)wic * RING_BYTES;
+    for (;;) {
+        unsigned long long j = 0;
+        if (lane == 0) j = atomicAdd(P.counter, 1ull);
+        j = __shfl_sync(FULL, j, 0);
+        if (j >= P.n_jobs) break;
+        const zxc_b200_job_t job = P.jobs[j];
+        const int r = decode_job(P, job, scratch, ring, lane);
+        __syncwarp();
+        if (lane == 0) P.status[j] = r;
+    }
+}
+
+/* status reduce: first job whose result differs from its dst_cap */
+__global__ void zxc_reduce_kernel(const i32* status, const zxc_b200_job_t* jobs, u32 n,
+                                  unsigned long long* out /* [0]=first bad idx, [1]=sum */) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long bad = ~0ull, sum = 0;
+    if (i < n) {
+        const i32 s = status[i];
+        if (s < 0 || (u32)s != jobs[i].dst_cap) bad = i;
+        else sum = (u32)s;
+    }
+    for (int d = 16; d >= 1; d >>= 1) {
+        const unsigned long long ob = __shfl_xor_sync(FULL, bad, d);
+        bad = ob < bad ? ob : bad;
+        sum += __shfl_xor_sync(FULL, sum, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (bad != ~0ull) atomicMin(&out[0], bad);
+        if (sum) atomicAdd(&out[1], sum);
+    }
+}
