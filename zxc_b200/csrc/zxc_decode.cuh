@@ -370,7 +370,54 @@ __device__ __forceinline__ void warp_match_global(const Window& w, u32 d, u32 of
     }
 }
 
-#define LIT_SHORT 16u
+/* ------------------------------------------------------------------------- */
+/* per-lane copy of n bytes (n <= 4*NWORDS - 4) into the ring, word granular:   */
+/* aligned 4-byte source words are funnel-shifted onto the destination's word   */
+/* grid; whole destination words go out as STS.32, the <= 3 + 3 edge bytes as   */
+/* byte stores (neighbouring lanes own the other bytes of those words).         */
+/* `sp` is a generic pointer (ring or global).  Caller guarantees: no ring wrap */
+/* on either side, and that sp - 7 is readable.                                 */
+/* ------------------------------------------------------------------------- */
+template <int NWORDS>
+__device__ __forceinline__ void lane_copy_words(u8* ring, u32 dpos, const u8* sp, u32 n, bool on) {
+    const u32 da = dpos & 3u;
+    u8* dbyte = ring + (dpos & (RING_BYTES - 1));
+    if (on) {
+        const u32 ff = da ? 1u : 0u;        /* first whole destination word */
+        const u32 lfe = (da + n) >> 2;      /* one past the last whole destination word */
+        const u32 tb = (da + n) & 3u;       /* bytes in the trailing partial word */
+        /* head bytes [da, min(4, da+n)) of destination word 0 */
+        if (da) {
+            const u32 hn = min(4u - da, n);
+            if (hn > 0) dbyte[0] = sp[0];
+            if (hn > 1) dbyte[1] = sp[1];
+            if (hn > 2) dbyte[2] = sp[2];
+        }
+        /* tail bytes of destination word lfe (unless the head already covered a lone word 0) */
+        if (tb && (lfe > 0 || da == 0)) {
+            const u32 t0 = n - tb;
+            dbyte[t0] = sp[t0];
+            if (tb > 1) dbyte[t0 + 1] = sp[t0 + 1];
+            if (tb > 2) dbyte[t0 + 2] = sp[t0 + 2];
+        }
+        if (lfe > ff) {
+            const u8* bp = sp - da;
+            const u32 m = (u32)(reinterpret_cast<uintptr_t>(bp)) & 3u;
+            const u32* wp = reinterpret_cast<const u32*>(bp - m);
+            u32* dw = reinterpret_cast<u32*>(dbyte - da);
+            const u32 sh = m * 8u;
+            const u32 nw = lfe + (m ? 1u : 0u);
+            u32 W[NWORDS + 1];
+#pragma unroll
+            for (int k = 0; k <= NWORDS; k++) W[k] = ((u32)k >= ff && (u32)k < nw) ? wp[k] : 0u;
+#pragma unroll
+            for (int k = 0; k < NWORDS; k++)
+                if ((u32)k >= ff && (u32)k < lfe) dw[k] = __funnelshift_r(W[k], W[k + 1], sh);
+        }
+    }
+}
+
+#define LIT_SHORT 20u
 #define MATCH_SHORT 32u
 
 /* ------------------------------------------------------------------------- */
@@ -487,10 +534,9 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
         }
 
         /* ---- literals: independent of every match ---- */
-        if (act && ll <= LIT_SHORT) {
-            for (u32 k = 0; k < ll; k++) ring[(out_start + k) & mask] = lit[lit_start + k];
-        }
-        u32 m_long = __ballot_sync(FULL, act && ll > LIT_SHORT);
+        const bool lit_fast = act && ll > 0 && ll <= LIT_SHORT && ((out_start & mask) + ll + 4 <= RING_BYTES);
+        lane_copy_words<6>(ring, out_start, lit + lit_start, ll, lit_fast);
+        u32 m_long = __ballot_sync(FULL, act && ll > 0 && !lit_fast);
         while (m_long) {
             const int j = __ffs(m_long) - 1;
             m_long &= m_long - 1;
@@ -508,10 +554,16 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
             const int first = __ffs(pending) - 1;
             const i32 W = (i32)__shfl_sync(FULL, mdst, first);
             const bool ready = ((pending >> lane) & 1u) && ((int)lane == first || src_end <= W);
-            if (ready && ml <= MATCH_SHORT) {
-                for (u32 k = 0; k < ml; k++) ring[(mdst + k) & mask] = window_byte(w, src_lo + (i32)k);
-            }
-            u32 m_lm = __ballot_sync(FULL, ready && ml > MATCH_SHORT);
+            /* per-lane word copy: short, not self-overlapping, source entirely in the ring or
+             * entirely flushed, no ring wrap on either side; everything else goes warp-wide */
+            const bool near = src_lo >= w.near_lo;
+            const bool fast = ready && ml <= MATCH_SHORT && off >= ml && src_lo >= 8 &&
+                              ((mdst & mask) + ml + 4 <= RING_BYTES) &&
+                              (!near || (((u32)src_lo & mask) >= 8 && ((u32)src_lo & mask) + ml + 8 <= RING_BYTES));
+            const u8* sp = near ? ring + ((u32)src_lo & mask) : out + src_lo;
+            if (__any_sync(FULL, fast && ml > 20u)) lane_copy_words<9>(ring, mdst, sp, ml, fast);
+            else lane_copy_words<6>(ring, mdst, sp, ml, fast);
+            u32 m_lm = __ballot_sync(FULL, ready && !fast);
             while (m_lm) {
                 const int j = __ffs(m_lm) - 1;
                 m_lm &= m_lm - 1;
@@ -564,7 +616,7 @@ __device__ int decode_job(const DecodeParams& P, const zxc_b200_job_t& job, u8* 
         case BT_GLO:
         case BT_GHI:
             return decode_lz_block(data, comp, type == BT_GHI, out, job.dst_cap, P.dict, P.dict_size,
-                                   P.dict_huf, scratch, P.scratch_stride, ring, lane);
+                                   P.dict_huf, scratch, P.scratch_stride - 256u, ring, lane);
         case BT_RAW:
             if (comp > job.dst_cap) return ZXC_ERROR_DST_TOO_SMALL;
             warp_copy(out, data, comp, lane);
@@ -581,7 +633,7 @@ __global__ void __launch_bounds__(CTA_THREADS) zxc_decode_kernel(const DecodePar
     const u32 lane = threadIdx.x & 31;
     const u32 wic = threadIdx.x >> 5;
     const u32 gwarp = blockIdx.x * WARPS_PER_CTA + wic;
-    u8* scratch = P.scratch + (size_t)gwarp * P.scratch_stride;
+    u8* scratch = P.scratch + (size_t)gwarp * P.scratch_stride + 256; /* lead-in: word loads may start below */
     u8* ring = smem + (size_t)wic * RING_BYTES;
     for (;;) {
         unsigned long long j = 0;

@@ -252,7 +252,8 @@ static int grid_for(u32 n_jobs) {
     return (int)(ctas_needed < resident ? ctas_needed : resident);
 }
 
-static u32 scratch_stride_for(u32 block_size) { return (block_size + 255u) & ~255u; }
+/* per-warp scratch for expanded literal sections; 256 bytes of lead-in so word loads may start below it */
+static u32 scratch_stride_for(u32 block_size) { return ((block_size + 255u) & ~255u) + 256u; }
 
 extern "C" size_t zxc_b200_decode_scratch_size(uint32_t block_size) {
     if (zxg_init() != ZXC_OK) return 0;
