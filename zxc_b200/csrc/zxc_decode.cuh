@@ -33,10 +33,10 @@ typedef int32_t i32;
 #define FULL 0xFFFFFFFFu
 #define WARPS_PER_CTA 4
 #define CTA_THREADS (WARPS_PER_CTA * 32)
-#define RING_BYTES 8192u          /* per-warp output ring (power of two, multiple of 512) */
+#define RING_BYTES 4096u          /* per-warp output ring (power of two, multiple of 512) */
 #define RING_LIMIT (RING_BYTES - 576u) /* largest output span one batch may add */
 #define DECODE_SMEM_BYTES (WARPS_PER_CTA * RING_BYTES)
-#define CTAS_PER_SM 7u            /* 227 KB / 32 KB of ring per CTA */
+#define CTAS_PER_SM 7u            /* register-limited (72 regs x 128 threads); 112 KB of rings, rest is L1 */
 
 #define BT_RAW 0
 #define BT_GLO 1
@@ -340,9 +340,56 @@ __device__ __forceinline__ void ring_flush(const Window& w, u32& F, u32 target, 
     F = target;
 }
 
+/* whole-warp copy of n bytes from a generic source pointer into the ring at dpos, 128 bytes per
+ * iteration: lane = destination word, two aligned source words funnel-shifted onto it.  Caller
+ * guarantees no ring wrap on the destination, sp - 7 readable, and that every 128-byte step only
+ * reads bytes that were complete before the step started (no self-overlap closer than 132). */
+__device__ __forceinline__ void warp_copy_words_to_ring(u8* ring, u32 dpos, const u8* sp, u32 n, u32 lane) {
+    const u32 da = dpos & 3u;
+    u8* dbyte = ring + (dpos & (RING_BYTES - 1));
+    const u32 ff = da ? 1u : 0u;
+    const u32 lfe = (da + n) >> 2;
+    const u32 tb = (da + n) & 3u;
+    /* edge bytes: lanes 0..2 the head, lanes 4..6 the tail */
+    if (da && lane < min(4u - da, n)) dbyte[lane] = sp[lane];
+    const u8* bp = sp - da;
+    const u32 m = (u32)(reinterpret_cast<uintptr_t>(bp)) & 3u;
+    const u32* wp = reinterpret_cast<const u32*>(bp - m);
+    u32* dw = reinterpret_cast<u32*>(dbyte - da);
+    const u32 sh = m * 8u;
+    for (u32 j0 = 0; j0 < lfe; j0 += 32) {
+        const u32 j = j0 + lane;
+        if (j >= ff && j < lfe) {
+            const u32 a = wp[j];
+            const u32 b = m ? wp[j + 1] : 0u;
+            dw[j] = __funnelshift_r(a, b, sh);
+        }
+        __syncwarp();
+    }
+    /* tail bytes last: with a self-overlapping source they are produced by the loop above */
+    if (tb && (lfe > 0 || da == 0) && lane < tb) {
+        const u32 t0 = n - tb + lane;
+        dbyte[t0] = sp[t0];
+    }
+}
+
 /* whole-warp match copy of n bytes into the ring at d from distance off */
 __device__ __forceinline__ void warp_match_to_ring(const Window& w, u32 d, u32 off, u32 n, u32 lane) {
     const u32 mask = RING_BYTES - 1;
+    const i32 s = (i32)d - (i32)off;
+    if (off >= 132 && s >= 8 && (d & mask) + n + 4 <= RING_BYTES) {
+        /* word path: the source is entirely in the ring (no wrap) or entirely flushed */
+        const u32 si = (u32)s & mask;
+        if (s >= w.near_lo) {
+            if (si >= 8 && si + n + 8 <= RING_BYTES) {
+                warp_copy_words_to_ring(w.ring, d, w.ring + si, n, lane);
+                return;
+            }
+        } else if (s + (i32)n + 4 <= w.near_lo) {
+            warp_copy_words_to_ring(w.ring, d, w.out + s, n, lane);
+            return;
+        }
+    }
     if (off >= 32) {
         /* chunk c only reads bytes below its own start: earlier chunks are complete */
         for (u32 c = 0; c < n; c += 32) {
@@ -473,13 +520,20 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
             const u32 ord_ll = __popc(m_ll & lt_mask) + __popc(m_ml & lt_mask);
             const u32 ord_ml = ord_ll + (e_ll ? 1u : 0u);
             k_esc = __popc(m_ll) + __popc(m_ml);
+            u32 my_pos = ext_end; /* cursor where this lane's first varint starts */
             for (u32 s = 0; s < k_esc; s++) {
                 if (s == lane) step_lo = epos_end;
                 if (s == lane + 32) step_hi = epos_end;
-                const u32 v = read_varint(ext, epos_end, ext_end);
-                if (e_ll && s == ord_ll) ll += v;
-                if (e_ml && s == ord_ml) ml += v;
+                if (s == ord_ll) my_pos = epos_end;
+                /* advance exactly as read_varint would (zxc_decompress.c:51-88) */
+                if (epos_end < ext_end) {
+                    const u32 b0 = ext[epos_end];
+                    const u32 len = 1u + (b0 >= 0x80u) + (b0 >= 0xC0u);
+                    epos_end = (b0 >= 0xE0u || epos_end + len > ext_end) ? ext_end : epos_end + len;
+                }
             }
+            if (e_ll) ll += read_varint(ext, my_pos, ext_end);
+            if (e_ml) ml += read_varint(ext, my_pos, ext_end);
         }
         if (valid) ml += 5;
         const u32 tot = ll + ml;
@@ -542,7 +596,8 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
             m_long &= m_long - 1;
             const u32 d = __shfl_sync(FULL, out_start, j), s = __shfl_sync(FULL, lit_start, j),
                       n = __shfl_sync(FULL, ll, j);
-            for (u32 k = lane; k < n; k += 32) ring[(d + k) & mask] = lit[s + k];
+            if ((d & mask) + n + 4 <= RING_BYTES) warp_copy_words_to_ring(ring, d, lit + s, n, lane);
+            else for (u32 k = lane; k < n; k += 32) ring[(d + k) & mask] = lit[s + k];
         }
         __syncwarp();
 
@@ -628,7 +683,7 @@ __device__ int decode_job(const DecodeParams& P, const zxc_b200_job_t& job, u8* 
     }
 }
 
-__global__ void __launch_bounds__(CTA_THREADS) zxc_decode_kernel(const DecodeParams P) {
+__global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) zxc_decode_kernel(const DecodeParams P) {
     extern __shared__ __align__(16) u8 smem[];
     const u32 lane = threadIdx.x & 31;
     const u32 wic = threadIdx.x >> 5;
