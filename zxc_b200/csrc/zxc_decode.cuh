@@ -376,20 +376,6 @@ __device__ __forceinline__ void warp_copy_words_to_ring(u8* ring, u32 dpos, cons
 /* whole-warp match copy of n bytes into the ring at d from distance off */
 __device__ __forceinline__ void warp_match_to_ring(const Window& w, u32 d, u32 off, u32 n, u32 lane) {
     const u32 mask = RING_BYTES - 1;
-    const i32 s = (i32)d - (i32)off;
-    if (off >= 132 && s >= 8 && (d & mask) + n + 4 <= RING_BYTES) {
-        /* word path: the source is entirely in the ring (no wrap) or entirely flushed */
-        const u32 si = (u32)s & mask;
-        if (s >= w.near_lo) {
-            if (si >= 8 && si + n + 8 <= RING_BYTES) {
-                warp_copy_words_to_ring(w.ring, d, w.ring + si, n, lane);
-                return;
-            }
-        } else if (s + (i32)n + 4 <= w.near_lo) {
-            warp_copy_words_to_ring(w.ring, d, w.out + s, n, lane);
-            return;
-        }
-    }
     if (off >= 32) {
         /* chunk c only reads bytes below its own start: earlier chunks are complete */
         for (u32 c = 0; c < n; c += 32) {
@@ -464,8 +450,61 @@ __device__ __forceinline__ void lane_copy_words(u8* ring, u32 dpos, const u8* sp
     }
 }
 
+/* ------------------------------------------------------------------------- */
+/* long items, four at a time: each 8-lane group copies one item into the ring,  */
+/* 32 bytes per step (lane = destination word).  Items of one call are mutually  */
+/* independent; an item may overlap itself only at distance >= 36.  Owners hold   */
+/* (dpos, generic source pointer, n) for their item; m_items has one bit per owner.*/
+/* ------------------------------------------------------------------------- */
+__device__ __forceinline__ void group4_copy_words(u8* ring, u32 m_items, u32 my_d, const u8* my_sp, u32 my_n,
+                                                  u32 lane) {
+    const u32 g = lane >> 3, sub = lane & 7u;
+    const unsigned long long my_sp64 = reinterpret_cast<unsigned long long>(my_sp);
+    while (m_items) {
+        int jsel = -1;
+#pragma unroll
+        for (u32 q = 0; q < 4; q++) {
+            const int j = m_items ? __ffs(m_items) - 1 : -1;
+            if (m_items) m_items &= m_items - 1;
+            if (q == g) jsel = j;
+        }
+        const bool on = jsel >= 0;
+        const int jj = on ? jsel : 0;
+        const u32 dpos = __shfl_sync(FULL, my_d, jj);
+        const u32 n_item = __shfl_sync(FULL, my_n, jj);
+        const u32 n = on ? n_item : 0u;
+        const u8* sp = reinterpret_cast<const u8*>(__shfl_sync(FULL, my_sp64, jj));
+        const u32 da = dpos & 3u;
+        u8* dbyte = ring + (dpos & (RING_BYTES - 1));
+        const u32 ff = da ? 1u : 0u;
+        const u32 lfe = (da + n) >> 2;
+        const u32 tb = (da + n) & 3u;
+        if (on && da && sub < min(4u - da, n)) dbyte[sub] = sp[sub];
+        const u8* bp = sp - da;
+        const u32 m = (u32)(reinterpret_cast<uintptr_t>(bp)) & 3u;
+        const u32* wp = reinterpret_cast<const u32*>(bp - m);
+        u32* dw = reinterpret_cast<u32*>(dbyte - da);
+        const u32 sh = m * 8u;
+        const u32 iters = __reduce_max_sync(FULL, (lfe + 7u) >> 3);
+        for (u32 it = 0; it < iters; it++) {
+            const u32 j = it * 8u + sub;
+            if (on && j >= ff && j < lfe) {
+                const u32 a = wp[j];
+                const u32 b = m ? wp[j + 1] : 0u;
+                dw[j] = __funnelshift_r(a, b, sh);
+            }
+            __syncwarp();
+        }
+        if (on && tb && (lfe > 0 || da == 0) && sub < tb) {
+            const u32 t0 = n - tb + sub;
+            dbyte[t0] = sp[t0];
+        }
+        __syncwarp();
+    }
+}
+
 #define LIT_SHORT 20u
-#define MATCH_SHORT 32u
+#define MATCH_SHORT 20u
 
 /* ------------------------------------------------------------------------- */
 /* GLO / GHI block body.  Returns decoded bytes or a negative zxc_error_t.    */
@@ -518,7 +557,6 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
         u32 step_lo = 0, step_hi = 0, k_esc = 0, epos_end = epos;
         if (m_ll | m_ml) {
             const u32 ord_ll = __popc(m_ll & lt_mask) + __popc(m_ml & lt_mask);
-            const u32 ord_ml = ord_ll + (e_ll ? 1u : 0u);
             k_esc = __popc(m_ll) + __popc(m_ml);
             u32 my_pos = ext_end; /* cursor where this lane's first varint starts */
             for (u32 s = 0; s < k_esc; s++) {
@@ -587,46 +625,66 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
             w.near_lo = a > (i32)ring_lo ? a : (i32)ring_lo;
         }
 
-        /* ---- literals: independent of every match ---- */
-        const bool lit_fast = act && ll > 0 && ll <= LIT_SHORT && ((out_start & mask) + ll + 4 <= RING_BYTES);
-        lane_copy_words<6>(ring, out_start, lit + lit_start, ll, lit_fast);
-        u32 m_long = __ballot_sync(FULL, act && ll > 0 && !lit_fast);
-        while (m_long) {
-            const int j = __ffs(m_long) - 1;
-            m_long &= m_long - 1;
-            const u32 d = __shfl_sync(FULL, out_start, j), s = __shfl_sync(FULL, lit_start, j),
-                      n = __shfl_sync(FULL, ll, j);
-            if ((d & mask) + n + 4 <= RING_BYTES) warp_copy_words_to_ring(ring, d, lit + s, n, lane);
-            else for (u32 k = lane; k < n; k += 32) ring[(d + k) & mask] = lit[s + k];
-        }
-        __syncwarp();
-
-        /* ---- matches: dependency rounds ---- */
-        u32 pending = __ballot_sync(FULL, act);
+        /* ---- copy passes: pass 0 = every literal run (independent of all matches), then match
+         * rounds: a match is ready once its source ends below the lowest pending match destination.
+         * One body serves all passes so the hot loop stays inside the instruction cache. ---- */
         const i32 src_lo = (i32)mdst - (i32)off;
         const i32 src_end = min((i32)mdst, src_lo + (i32)ml);
-        while (pending) {
-            const int first = __ffs(pending) - 1;
-            const i32 W = (i32)__shfl_sync(FULL, mdst, first);
-            const bool ready = ((pending >> lane) & 1u) && ((int)lane == first || src_end <= W);
-            /* per-lane word copy: short, not self-overlapping, source entirely in the ring or
-             * entirely flushed, no ring wrap on either side; everything else goes warp-wide */
-            const bool near = src_lo >= w.near_lo;
-            const bool fast = ready && ml <= MATCH_SHORT && off >= ml && src_lo >= 8 &&
-                              ((mdst & mask) + ml + 4 <= RING_BYTES) &&
-                              (!near || (((u32)src_lo & mask) >= 8 && ((u32)src_lo & mask) + ml + 8 <= RING_BYTES));
-            const u8* sp = near ? ring + ((u32)src_lo & mask) : out + src_lo;
-            if (__any_sync(FULL, fast && ml > 20u)) lane_copy_words<9>(ring, mdst, sp, ml, fast);
-            else lane_copy_words<6>(ring, mdst, sp, ml, fast);
-            u32 m_lm = __ballot_sync(FULL, ready && !fast);
-            while (m_lm) {
-                const int j = __ffs(m_lm) - 1;
-                m_lm &= m_lm - 1;
-                warp_match_to_ring(w, __shfl_sync(FULL, mdst, j), __shfl_sync(FULL, off, j),
-                                   __shfl_sync(FULL, ml, j), lane);
+        /* word copies need: no ring wrap on the destination, and a source that is entirely in the
+         * ring (no wrap) or entirely flushed to global memory */
+        const bool near = src_lo >= w.near_lo;
+        const u32 si = (u32)src_lo & mask;
+        const bool m_word_ok = ((mdst & mask) + ml + 4 <= RING_BYTES) &&
+                               (near ? (si >= 8 && si + ml + 8 <= RING_BYTES)
+                                     : (src_lo >= 8 && src_lo + (i32)ml + 4 <= w.near_lo));
+        const bool m_lane_ok = m_word_ok && ml <= MATCH_SHORT && off >= ml;
+        const bool m_grp_ok = m_word_ok && !m_lane_ok && off >= 36;
+        const u8* m_sp = near ? ring + si : out + src_lo;
+        const bool l_word_ok = (out_start & mask) + ll + 4 <= RING_BYTES;
+
+        u32 pending = __ballot_sync(FULL, act);
+        bool lit_pass = true;
+#pragma unroll 1
+        for (;;) {
+            bool ready, lok, gok;
+            u32 it_d, it_n;
+            const u8* it_sp;
+            if (lit_pass) {
+                ready = act && ll > 0;
+                it_d = out_start;
+                it_n = ll;
+                it_sp = lit + lit_start;
+                lok = l_word_ok && ll <= LIT_SHORT;
+                gok = l_word_ok && ll > LIT_SHORT;
+            } else {
+                const int first = __ffs(pending) - 1;
+                const i32 W = (i32)__shfl_sync(FULL, mdst, first);
+                ready = ((pending >> lane) & 1u) && ((int)lane == first || src_end <= W);
+                it_d = mdst;
+                it_n = ml;
+                it_sp = m_sp;
+                lok = m_lane_ok;
+                gok = m_grp_ok;
             }
-            pending &= ~__ballot_sync(FULL, ready);
+            lane_copy_words<6>(ring, it_d, it_sp, it_n, ready && lok);
+            const u32 m_grp = __ballot_sync(FULL, ready && gok);
+            if (m_grp) group4_copy_words(ring, m_grp, it_d, it_sp, it_n, lane);
+            u32 m_slow = __ballot_sync(FULL, ready && !lok && !gok);
+            while (m_slow) { /* ring wrap, close overlap, dictionary, straddling sources: byte paths */
+                const int j = __ffs(m_slow) - 1;
+                m_slow &= m_slow - 1;
+                const u32 d = __shfl_sync(FULL, it_d, j), n = __shfl_sync(FULL, it_n, j);
+                const u32 aux = __shfl_sync(FULL, lit_pass ? lit_start : off, j);
+                if (lit_pass) {
+                    for (u32 k = lane; k < n; k += 32) ring[(d + k) & mask] = lit[aux + k];
+                } else {
+                    warp_match_to_ring(w, d, aux, n, lane);
+                }
+            }
             __syncwarp();
+            if (lit_pass) lit_pass = false;
+            else pending &= ~__ballot_sync(FULL, ready);
+            if (!pending) break;
         }
 
         O += T;
