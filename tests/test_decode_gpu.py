@@ -220,3 +220,22 @@ def test_large_roundtrip_properties(prod, ref):
     assert prod.lib.zxc_seekable_decompress_range_mt(h, part.ctypes.data, part.size, 100 << 20, part.size, 0) == part.size
     assert np.array_equal(part, data[100 << 20:164 << 20])
     prod.lib.zxc_seekable_free(h)
+
+
+def test_pinned_pipelined_frame_path(prod, ref):
+    """Page-locked caller buffers take the chunked H2D / decode / D2H pipeline (zxg_decode_pipelined)."""
+    torch = pytest.importorskip("torch")
+    n = 200 << 20
+    data = zc.silesia_shaped(n, seed=33)
+    frame = zc.compress_ref_mt(ref, data, level=3, block_size=65536, checksum=1)
+    h_frame = torch.from_numpy(frame).pin_memory()
+    h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
+    o = z.DecompressOpts(checksum_enabled=1)
+    r = prod.lib.zxc_decompress(h_frame.data_ptr(), h_frame.numel(), h_out.data_ptr(), n, C.byref(o))
+    assert r == n
+    assert np.array_equal(h_out.numpy(), data)
+    # a damaged block in a late chunk is still reported with the reference's code
+    f2 = h_frame.clone().pin_memory()
+    f2[int(f2.numel() * 0.9)] ^= 0x10
+    r0, _ = ref.decompress(f2.numpy(), n, checksum=1)
+    assert prod.lib.zxc_decompress(f2.data_ptr(), f2.numel(), h_out.data_ptr(), n, C.byref(o)) == r0 < 0

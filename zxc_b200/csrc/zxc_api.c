@@ -390,6 +390,16 @@ static int64_t decompress_frame(zxg_ctx* g, const uint8_t* src, size_t src_size,
         if (!status) { ret = ZXC_ERROR_MEMORY; goto out; }
         const uint64_t src_lo = w.jobs[0].src_off;
         const uint64_t src_hi = w.jobs[n_fit - 1].src_off + w.jobs[n_fit - 1].src_len;
+        if (produced >= ((uint64_t)32 << 20) && zxg_host_pinned(src) && zxg_host_pinned(dst)) {
+            /* page-locked caller buffers: overlap H2D, decode and D2H chunk by chunk */
+            const int prc = zxg_decode_pipelined(g, src, src_lo, src_hi, dst, produced, w.jobs, (uint32_t)n_fit, status,
+                                                 dict, (uint32_t)dict_size, dict_huf, w.block_size, verify);
+            if (prc != ZXC_OK) { ret = prc; goto out; }
+            int mm = 0;
+            const int64_t pf = first_failure(status, w.jobs, n_fit, &mm);
+            if (pf < 0) { ret = pf; goto out; }
+            goto decoded;
+        }
         uint8_t* d_in = (uint8_t*)zxg_buffer(g, ZXG_BUF_IN, (size_t)(src_hi - src_lo) + 16);
         uint8_t* d_out = (uint8_t*)zxg_buffer(g, ZXG_BUF_OUT, (size_t)produced + 16);
         if (!d_in || !d_out) { ret = ZXC_ERROR_MEMORY; goto out; }
@@ -406,6 +416,7 @@ static int64_t decompress_frame(zxg_ctx* g, const uint8_t* src, size_t src_size,
         rc = zxg_d2h(g, dst, d_out, (size_t)produced);
         if (rc != ZXC_OK) { ret = rc; goto out; }
     }
+decoded:
     if (n_fit < w.n_jobs) { ret = ZXC_ERROR_DST_TOO_SMALL; goto out; }
     if (w.end == ZXW_END_BAD_HEADER) { ret = ZXC_ERROR_BAD_HEADER; goto out; }
     if (w.end == ZXW_END_EOF) {

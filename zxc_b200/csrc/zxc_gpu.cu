@@ -48,6 +48,7 @@ struct zxg_ctx {
     void* pin[2];
     cudaEvent_t pin_ev[2];
     unsigned long long* counter; /* [0] work counter, [1..2] reduce output */
+    cudaStream_t s_h2d, s_d2h;   /* copy engines for the pipelined frame path (lazily created) */
     struct zxg_ctx* next;
     int device;
 };
@@ -111,6 +112,8 @@ extern "C" void zxg_destroy(zxg_ctx* c) {
         if (c->pin_ev[i]) cudaEventDestroy(c->pin_ev[i]);
     }
     cudaFree(c->counter);
+    if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+    if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
     cudaStreamDestroy(c->stream);
     free(c);
 }
@@ -366,4 +369,87 @@ extern "C" int zxg_decode_jobs(zxg_ctx* c, const void* d_src, void* d_dst, const
         return ZXC_B200_ERROR_CUDA;
     }
     return ZXC_OK;
+}
+
+
+/* ------------------------------------------------------------------------- */
+/* Pipelined frame decode for page-locked host buffers: the frame is cut into  */
+/* chunks of whole blocks; chunk k's H2D copy, chunk k-1's decode and chunk     */
+/* k-2's D2H copy run concurrently on three streams (both PCIe directions and   */
+/* the SMs busy at once).  Pageable buffers take the staged path instead.       */
+/* ------------------------------------------------------------------------- */
+extern "C" int zxg_host_pinned(const void* p) { return host_is_pinned(p); }
+
+extern "C" int zxg_decode_pipelined(zxg_ctx* c, const uint8_t* h_src, uint64_t src_lo, uint64_t src_hi,
+                                    uint8_t* h_dst, uint64_t produced, const zxc_b200_job_t* h_jobs,
+                                    uint32_t n_jobs, int32_t* h_status, const void* h_dict, uint32_t dict_size,
+                                    const void* h_dict_huf, uint32_t block_size, int verify_checksums) {
+    if (n_jobs == 0) return ZXC_OK;
+    if (!c->s_h2d && cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking) != cudaSuccess) return ZXC_B200_ERROR_CUDA;
+    if (!c->s_d2h && cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking) != cudaSuccess) return ZXC_B200_ERROR_CUDA;
+    u8* d_in = (u8*)zxg_buffer(c, ZXG_BUF_IN, (size_t)(src_hi - src_lo) + 16);
+    u8* d_out = (u8*)zxg_buffer(c, ZXG_BUF_OUT, (size_t)produced + 16);
+    zxc_b200_job_t* d_jobs = (zxc_b200_job_t*)zxg_buffer(c, ZXG_BUF_JOBS, (size_t)n_jobs * sizeof(zxc_b200_job_t));
+    i32* d_status = (i32*)zxg_buffer(c, ZXG_BUF_STATUS, (size_t)n_jobs * sizeof(i32));
+    const size_t warps = (size_t)grid_for(n_jobs) * WARPS_PER_CTA;
+    const size_t scratch_size = warps * scratch_stride_for(block_size);
+    void* d_scratch = zxg_buffer(c, ZXG_BUF_SCRATCH, scratch_size);
+    if (!d_in || !d_out || !d_jobs || !d_status || !d_scratch) return ZXC_ERROR_MEMORY;
+    u8* d_dict = NULL;
+    u8* d_huf = NULL;
+    if (h_dict && dict_size) {
+        d_dict = (u8*)zxg_buffer(c, ZXG_BUF_DICT, (size_t)dict_size + 128);
+        if (!d_dict) return ZXC_ERROR_MEMORY;
+        int rc = zxg_h2d(c, d_dict, h_dict, dict_size);
+        if (rc == ZXC_OK && h_dict_huf) {
+            d_huf = d_dict + dict_size;
+            rc = zxg_h2d(c, d_huf, h_dict_huf, 128);
+        }
+        if (rc != ZXC_OK) return rc;
+    }
+    if (cudaMemcpyAsync(d_jobs, h_jobs, (size_t)n_jobs * sizeof(zxc_b200_job_t), cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+        return ZXC_B200_ERROR_CUDA;
+
+    const uint64_t chunk_target = (uint64_t)64 << 20; /* decoded bytes per pipeline stage */
+    cudaEvent_t ev_in, ev_dec;
+    int rc = ZXC_OK;
+    uint32_t j0 = 0;
+    while (j0 < n_jobs && rc == ZXC_OK) {
+        uint32_t j1 = j0;
+        uint64_t acc = 0;
+        while (j1 < n_jobs && acc < chunk_target) acc += h_jobs[j1++].dst_cap;
+        const uint64_t s0 = h_jobs[j0].src_off, s1 = h_jobs[j1 - 1].src_off + h_jobs[j1 - 1].src_len;
+        const uint64_t o0 = h_jobs[j0].dst_off, o1 = h_jobs[j1 - 1].dst_off + h_jobs[j1 - 1].dst_cap;
+        if (cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ev_dec, cudaEventDisableTiming) != cudaSuccess) {
+            rc = ZXC_B200_ERROR_CUDA;
+            break;
+        }
+        if (cudaMemcpyAsync(d_in + (s0 - src_lo), h_src + s0, (size_t)(s1 - s0), cudaMemcpyHostToDevice, c->s_h2d) != cudaSuccess)
+            rc = ZXC_B200_ERROR_CUDA;
+        cudaEventRecord(ev_in, c->s_h2d);
+        cudaStreamWaitEvent(c->stream, ev_in, 0);
+        if (rc == ZXC_OK)
+            rc = launch_decode(d_in - src_lo, d_out, d_jobs + j0, j1 - j0, d_status + j0, d_dict, dict_size, d_huf,
+                               d_scratch, scratch_size, block_size, verify_checksums, c->counter, c->stream);
+        cudaEventRecord(ev_dec, c->stream);
+        cudaStreamWaitEvent(c->s_d2h, ev_dec, 0);
+        if (rc == ZXC_OK &&
+            cudaMemcpyAsync(h_dst + o0, d_out + o0, (size_t)(o1 - o0), cudaMemcpyDeviceToHost, c->s_d2h) != cudaSuccess)
+            rc = ZXC_B200_ERROR_CUDA;
+        cudaEventDestroy(ev_in); /* deferred by the runtime until the events complete */
+        cudaEventDestroy(ev_dec);
+        j0 = j1;
+    }
+    if (rc == ZXC_OK &&
+        cudaMemcpyAsync(h_status, d_status, (size_t)n_jobs * sizeof(i32), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+        rc = ZXC_B200_ERROR_CUDA;
+    const cudaError_t e1 = cudaStreamSynchronize(c->stream);
+    const cudaError_t e2 = cudaStreamSynchronize(c->s_d2h);
+    const cudaError_t e3 = cudaStreamSynchronize(c->s_h2d);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+        fprintf(stderr, "libzxc (B200 build): pipelined decode failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+        return ZXC_B200_ERROR_CUDA;
+    }
+    return rc;
 }

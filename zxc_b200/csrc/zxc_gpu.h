@@ -46,6 +46,17 @@ int zxg_decode_jobs(zxg_ctx* c, const void* d_src, void* d_dst, const zxc_b200_j
                     uint32_t n_jobs, int32_t* h_status, const void* h_dict, uint32_t dict_size,
                     const void* h_dict_huf, uint32_t block_size, int verify_checksums);
 
+/* 1 when the pointer is page-locked (cudaHostAlloc / cudaHostRegister / managed) */
+int zxg_host_pinned(const void* p);
+
+/* Frame decode with H2D / decode / D2H overlapped over chunks of whole blocks; both host
+ * buffers must be page-locked.  Job offsets are relative to h_src / h_dst; h_status gets
+ * n_jobs entries.  The output is copied back even for failing jobs (caller decides). */
+int zxg_decode_pipelined(zxg_ctx* c, const uint8_t* h_src, uint64_t src_lo, uint64_t src_hi, uint8_t* h_dst,
+                         uint64_t produced, const zxc_b200_job_t* h_jobs, uint32_t n_jobs, int32_t* h_status,
+                         const void* h_dict, uint32_t dict_size, const void* h_dict_huf, uint32_t block_size,
+                         int verify_checksums);
+
 #ifdef __cplusplus
 }
 #endif
