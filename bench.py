@@ -240,6 +240,8 @@ def main():
                                         None, 0, None, d_scratch.data_ptr(), scratch_size, BLOCK, 0, stream.cuda_stream)
         assert rc == 0, rc
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()  # nvidia-smi takes ~0.5 s to deliver its first line: start it ahead of the warm-up
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize(dev)
@@ -250,8 +252,11 @@ def main():
         assert np.array_equal(got, data), "decoded bytes differ from the original"
         del got
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    t_wait = time.time()
+    while len(sampler.lines) < 2 and time.time() - t_wait < 3.0:
+        step()  # keep the GPU under load until the sampler is live (untimed)
+        torch.cuda.synchronize(dev)
+    sampler.lines.clear()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
