@@ -555,16 +555,63 @@ int64_t zxc_decompress_block_safe(zxc_dctx* dctx, const void* src, const size_t 
 /* encode entry points: the match-finder kernel is not in this build yet.    */
 /* They fail loudly instead of falling back to a CPU encoder.                */
 /* ------------------------------------------------------------------------- */
+static int64_t compress_frame(zxg_ctx* g, const uint8_t* src, size_t src_size, uint8_t* dst, size_t dst_capacity,
+                              int level, size_t block_size, int checksum, int seekable) {
+    const uint64_t nb64 = (src_size + block_size - 1) / block_size;
+    if (nb64 > 0xFFFFFFFFull - 2) return ZXC_ERROR_BAD_BLOCK_SIZE;
+    const uint32_t nb = (uint32_t)nb64;
+    const size_t trailer = ZXF_BLOCK_HDR + ((seekable && nb > 0) ? zxc_seek_table_size(nb) : 0) + ZXC_FILE_FOOTER_SIZE;
+    if (dst_capacity < ZXC_FILE_HEADER_SIZE + trailer) return ZXC_ERROR_DST_TOO_SMALL;
+    int r = zxf_write_file_header(dst, dst_capacity, block_size, checksum, 0);
+    if (r < 0) return r;
+    uint32_t* sizes = nb ? (uint32_t*)malloc((size_t)nb * sizeof *sizes) : NULL;
+    if (nb && !sizes) return ZXC_ERROR_MEMORY;
+    uint64_t body = 0;
+    const uint64_t body_cap = dst_capacity - ZXC_FILE_HEADER_SIZE - trailer;
+    const int rc = zxg_encode_body(g, src, src_size, (uint32_t)block_size, level, checksum, nb,
+                                   dst + ZXC_FILE_HEADER_SIZE, body_cap, sizes, &body);
+    if (rc != ZXC_OK) {
+        free(sizes);
+        return rc;
+    }
+    uint8_t* op = dst + ZXC_FILE_HEADER_SIZE + body;
+    uint32_t ghash = 0;
+    if (checksum) { /* global hash: rotate-xor fold of the per-block checksums, in order (:751-758) */
+        const uint8_t* bp = dst + ZXC_FILE_HEADER_SIZE;
+        for (uint32_t i = 0; i < nb; i++) {
+            bp += sizes[i];
+            ghash = zxf_hash_combine(ghash, zxf_le32(bp - ZXF_BLOCK_CKS));
+        }
+    }
+    op += zxf_write_block_header(op, ZXF_BLOCK_HDR, ZXF_BT_EOF, 0);
+    if (seekable && nb > 0) op += zxc_write_seek_table(op, zxc_seek_table_size(nb), sizes, nb);
+    op += zxf_write_footer(op, ZXC_FILE_FOOTER_SIZE, src_size, ghash, checksum);
+    free(sizes);
+    return (int64_t)(op - dst);
+}
+
 int64_t zxc_compress(const void* src, const size_t src_size, void* dst, const size_t dst_capacity,
                      const zxc_compress_opts_t* opts) {
     if (!dst || dst_capacity == 0 || (src_size > 0 && !src)) return ZXC_ERROR_NULL_INPUT;
+    const int checksum = opts ? opts->checksum_enabled : 0;
+    const int seekable = opts ? opts->seekable : 0;
+    const int level = level_clamp(opts ? opts->level : 0);
     const size_t dict_size = (opts && opts->dict) ? opts->dict_size : 0;
     const size_t block_size = (opts && opts->block_size) ? opts->block_size : ZXC_BLOCK_SIZE_DEFAULT;
     if (dict_size > ZXC_DICT_SIZE_MAX) return ZXC_ERROR_DICT_TOO_LARGE;
     if (!zxf_valid_block_size(block_size)) return ZXC_ERROR_BAD_BLOCK_SIZE;
     const int irc = zxg_init();
     if (irc != ZXC_OK) return irc;
-    return ZXC_B200_ERROR_UNSUPPORTED;
+    /* on the GPU this round: the greedy / lazy parsers of levels 1-5 without a dictionary; the
+     * optimal parser + PivCo entropy stage (levels 6-7) and dictionary seeding are not (no CPU
+     * fallback: refuse loudly) */
+    if (level >= ZXC_LEVEL_DENSITY || dict_size > 0) return ZXC_B200_ERROR_UNSUPPORTED;
+    zxg_ctx* g = zxg_acquire();
+    if (!g) return ZXC_ERROR_MEMORY;
+    const int64_t r = compress_frame(g, (const uint8_t*)src, src_size, (uint8_t*)dst, dst_capacity, level, block_size,
+                                     checksum, seekable);
+    zxg_release(g);
+    return r;
 }
 
 int64_t zxc_compress_cctx(zxc_cctx* cctx, const void* src, size_t src_size, void* dst, size_t dst_capacity,

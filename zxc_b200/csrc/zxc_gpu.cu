@@ -29,6 +29,7 @@
 #include "zxc_gpu.h"
 
 #include "zxc_decode.cuh"
+#include "zxc_encode.cuh"
 
 /* ========================================================================= */
 /* host side: device bring-up, contexts, copies, launches                    */
@@ -451,5 +452,88 @@ extern "C" int zxg_decode_pipelined(zxg_ctx* c, const uint8_t* h_src, uint64_t s
         fprintf(stderr, "libzxc (B200 build): pipelined decode failed: %s\n", cudaGetErrorString(cudaGetLastError()));
         return ZXC_B200_ERROR_CUDA;
     }
+    return rc;
+}
+
+
+/* ------------------------------------------------------------------------- */
+/* frame body encode: blocks -> per-block slots -> compacted body             */
+/* ------------------------------------------------------------------------- */
+static u32 enc_staging_stride(u32 bs) { return ((bs + 8u + 68u + 4u) + 255u) & ~255u; }
+static size_t enc_scratch_stride(u32 bs) {
+    const size_t seq_cap = bs / 5 + 32;
+    size_t n = (size_t)ENC_HASH_SIZE * 4 + (size_t)ENC_WINDOW * 2 + (((size_t)bs + 63) & ~(size_t)63) + 64 +
+               seq_cap * 4 + bs / 4 + 64;
+    return (n + 255) & ~(size_t)255;
+}
+
+/* Encodes src into the frame BODY (all data blocks back to back) in h_body.  h_sizes receives
+ * n_blocks on-disk block sizes.  Returns ZXC_OK, or ZXC_ERROR_DST_TOO_SMALL when the body does
+ * not fit body_cap (then *body_size holds the size that would have been needed). */
+extern "C" int zxg_encode_body(zxg_ctx* c, const uint8_t* h_src, uint64_t src_size, uint32_t block_size, int level,
+                               int checksum, uint32_t n_blocks, uint8_t* h_body, uint64_t body_cap,
+                               uint32_t* h_sizes, uint64_t* body_size) {
+    *body_size = 0;
+    if (n_blocks == 0) return ZXC_OK;
+    const u32 sstride = enc_staging_stride(block_size);
+    const size_t wstride = enc_scratch_stride(block_size);
+    const u32 ctas_needed = (n_blocks + ENC_WARPS_PER_CTA - 1) / ENC_WARPS_PER_CTA;
+    const u32 resident = (u32)(g_sm_count > 0 ? g_sm_count : 148) * 3u;
+    const u32 grid = ctas_needed < resident ? ctas_needed : resident;
+    u8* d_src = (u8*)zxg_buffer(c, ZXG_BUF_IN, (size_t)src_size + 64);
+    u8* d_stage = (u8*)zxg_buffer(c, ZXG_BUF_OUT, (size_t)n_blocks * sstride);
+    u8* d_scratch = (u8*)zxg_buffer(c, ZXG_BUF_SCRATCH, (size_t)grid * ENC_WARPS_PER_CTA * wstride);
+    u32* d_sizes = (u32*)zxg_buffer(c, ZXG_BUF_STATUS, (size_t)n_blocks * 4);
+    unsigned long long* d_offs = (unsigned long long*)zxg_buffer(c, ZXG_BUF_JOBS, (size_t)n_blocks * 8);
+    if (!d_src || !d_stage || !d_scratch || !d_sizes || !d_offs) return ZXC_ERROR_MEMORY;
+    int rc = zxg_h2d(c, d_src, h_src, (size_t)src_size);
+    if (rc != ZXC_OK) return rc;
+    if (cudaMemsetAsync(d_src + src_size, 0, 64, c->stream) != cudaSuccess) return ZXC_B200_ERROR_CUDA;
+    EncodeParams P;
+    P.src = d_src;
+    P.staging = d_stage;
+    P.out_size = d_sizes;
+    P.scratch = d_scratch;
+    P.counter = c->counter;
+    P.dict = NULL;
+    P.src_size = src_size;
+    P.scratch_stride = wstride;
+    P.block_size = block_size;
+    P.n_blocks = n_blocks;
+    P.staging_stride = sstride;
+    P.level = (u32)level;
+    P.checksum = checksum ? 1u : 0u;
+    P.dict_size = 0;
+    if (cudaMemsetAsync(c->counter, 0, sizeof(unsigned long long), c->stream) != cudaSuccess) return ZXC_B200_ERROR_CUDA;
+    zxc_encode_kernel<<<grid, ENC_CTA_THREADS, 0, c->stream>>>(P);
+    __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
+    if (cudaMemcpyAsync(h_sizes, d_sizes, (size_t)n_blocks * 4, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess) {
+        fprintf(stderr, "libzxc (B200 build): encode kernel failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+        return ZXC_B200_ERROR_CUDA;
+    }
+    unsigned long long* h_offs = (unsigned long long*)malloc((size_t)n_blocks * 8);
+    if (!h_offs) return ZXC_ERROR_MEMORY;
+    uint64_t acc = 0;
+    for (u32 i = 0; i < n_blocks; i++) {
+        h_offs[i] = acc;
+        acc += h_sizes[i];
+    }
+    *body_size = acc;
+    if (acc > body_cap) {
+        free(h_offs);
+        return ZXC_ERROR_DST_TOO_SMALL;
+    }
+    /* the input buffer is no longer needed: reuse it for the compacted body when it is big enough */
+    u8* d_body = (u8*)zxg_buffer(c, ZXG_BUF_AUX, (size_t)acc + 16);
+    rc = d_body ? zxg_h2d(c, d_offs, h_offs, (size_t)n_blocks * 8) : ZXC_ERROR_MEMORY;
+    if (rc == ZXC_OK) {
+        const u32 cgrid = (n_blocks + 7) / 8 < 148u * 8u ? (n_blocks + 7) / 8 : 148u * 8u;
+        zxc_compact_kernel<<<cgrid, 256, 0, c->stream>>>(d_stage, sstride, d_offs, d_sizes, d_body, n_blocks);
+        __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
+        rc = zxg_d2h(c, h_body, d_body, (size_t)acc);
+        if (rc == ZXC_OK) rc = zxg_sync(c);
+    }
+    free(h_offs);
     return rc;
 }
