@@ -59,8 +59,17 @@ def test_golden_encoder_kat(prod):
             out[i] = next(g) >> 24
         return out
 
+    multiblock = text(5 * 4096 + 777)
     cases = {  # name: (data, level, block_size, checksum, seekable)   tests/format/golden_cases.h
-        "01_empty_eof_only.zxc": (np.zeros(0, np.uint8), 3, 0, 0, 0),
+        "01_empty_eof_only.zxc": (np.zeros(0, np.uint8), 1, 0, 0, 0),
+        "02_block_raw.zxc": (raw4096(), 1, 0, 0, 0),
+        "03_block_ghi.zxc": (text(8192), 1, 0, 0, 0),
+        "04_block_glo.zxc": (text(8192), 3, 0, 0, 0),
+        "06_checksum_per_block.zxc": (text(8192), 3, 0, 1, 0),
+        "07_multiple_blocks.zxc": (multiblock, 3, 4096, 1, 0),
+        "08_seekable_table.zxc": (multiblock, 3, 4096, 1, 1),
+        "10_glo_offset16.zxc": (offset16(), 3, 0, 0, 0),
+        "11_glo_rle.zxc": (rle_lits(), 3, 0, 0, 0),
     }
     got = {}
     for name, (data, level, bs, cks, seek) in cases.items():
@@ -78,3 +87,26 @@ def test_roundtrip_through_own_decoder(prod):
         assert not isinstance(fr, int)
         r, out = prod.decompress(fr, data.size, checksum=1)
         assert r == data.size and np.array_equal(out, data)
+
+
+def test_dictionary_frames_identical_to_reference(prod, ref):
+    from test_oracle import GC_DICT
+    rng = np.random.default_rng(12)
+    words = [b'"user_id":', b'"timestamp":', b'"status":"ok"', b'"payload":{', b'"region":"eu-west"', b'},{']
+    dict16k = b"".join(words[i % len(words)] + b"," for i in range(2000))[:16384]
+    recs = b"".join(b"{" + b",".join(words[int(k)] + str(int(v)).encode() for k, v in zip(rng.integers(0, 6, 20), rng.integers(0, 1 << 20, 20))) + b"}\n"
+                    for _ in range(3000))
+    data = np.frombuffer(recs, np.uint8)
+    for d in (dict16k, GC_DICT, dict16k[:7], dict16k[:5], bytes(rng.integers(0, 256, 65535, dtype=np.uint8))):
+        for level, bs in ((5, 4096), (3, 65536), (1, 4096), (2, 8192), (4, 1 << 20)):
+            a = ref.compress(data, level=level, block_size=bs, seekable=1, checksum=1, dict=d)
+            b = prod.compress(data, level=level, block_size=bs, seekable=1, checksum=1, dict=d)
+            assert not isinstance(b, int), (level, bs, len(d), z.ERR.get(b, b))
+            assert a.size == b.size and np.array_equal(a, b), (level, bs, len(d))
+    # golden 09_block_dict
+    req = (b"GET /api/v1/users/4242/profile HTTP/1.1\r\nHost: api.example.com\r\n"
+           b"Accept: application/json\r\nUser-Agent: zxc-client\r\n\r\n")
+    payload = np.frombuffer(bytes(req[i % len(req)] for i in range(4096)), np.uint8)
+    fr = prod.compress(payload, level=3, dict=GC_DICT)
+    want = [l.split()[0] for l in open(os.path.join(G, "format", "golden.sha256")) if "09_block_dict" in l][0]
+    assert hashlib.sha256(fr.tobytes()).hexdigest() == want

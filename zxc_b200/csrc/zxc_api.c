@@ -556,20 +556,22 @@ int64_t zxc_decompress_block_safe(zxc_dctx* dctx, const void* src, const size_t 
 /* They fail loudly instead of falling back to a CPU encoder.                */
 /* ------------------------------------------------------------------------- */
 static int64_t compress_frame(zxg_ctx* g, const uint8_t* src, size_t src_size, uint8_t* dst, size_t dst_capacity,
-                              int level, size_t block_size, int checksum, int seekable) {
+                              int level, size_t block_size, int checksum, int seekable, const uint8_t* dict,
+                              size_t dict_size, const uint8_t* dict_huf) {
     const uint64_t nb64 = (src_size + block_size - 1) / block_size;
     if (nb64 > 0xFFFFFFFFull - 2) return ZXC_ERROR_BAD_BLOCK_SIZE;
     const uint32_t nb = (uint32_t)nb64;
     const size_t trailer = ZXF_BLOCK_HDR + ((seekable && nb > 0) ? zxc_seek_table_size(nb) : 0) + ZXC_FILE_FOOTER_SIZE;
     if (dst_capacity < ZXC_FILE_HEADER_SIZE + trailer) return ZXC_ERROR_DST_TOO_SMALL;
-    int r = zxf_write_file_header(dst, dst_capacity, block_size, checksum, 0);
+    const uint32_t did = (dict && dict_size) ? zxc_dict_id(dict, dict_size, dict_huf) : 0;
+    int r = zxf_write_file_header(dst, dst_capacity, block_size, checksum, did);
     if (r < 0) return r;
     uint32_t* sizes = nb ? (uint32_t*)malloc((size_t)nb * sizeof *sizes) : NULL;
     if (nb && !sizes) return ZXC_ERROR_MEMORY;
     uint64_t body = 0;
     const uint64_t body_cap = dst_capacity - ZXC_FILE_HEADER_SIZE - trailer;
     const int rc = zxg_encode_body(g, src, src_size, (uint32_t)block_size, level, checksum, nb,
-                                   dst + ZXC_FILE_HEADER_SIZE, body_cap, sizes, &body);
+                                   dst + ZXC_FILE_HEADER_SIZE, body_cap, sizes, &body, dict, (uint32_t)dict_size);
     if (rc != ZXC_OK) {
         free(sizes);
         return rc;
@@ -602,14 +604,15 @@ int64_t zxc_compress(const void* src, const size_t src_size, void* dst, const si
     if (!zxf_valid_block_size(block_size)) return ZXC_ERROR_BAD_BLOCK_SIZE;
     const int irc = zxg_init();
     if (irc != ZXC_OK) return irc;
-    /* on the GPU this round: the greedy / lazy parsers of levels 1-5 without a dictionary; the
-     * optimal parser + PivCo entropy stage (levels 6-7) and dictionary seeding are not (no CPU
-     * fallback: refuse loudly) */
-    if (level >= ZXC_LEVEL_DENSITY || dict_size > 0) return ZXC_B200_ERROR_UNSUPPORTED;
+    /* on the GPU this round: the greedy / lazy parsers of levels 1-5, with or without a dictionary; the
+     * optimal parser + PivCo entropy stage (levels 6-7) are not (no CPU fallback: refuse loudly) */
+    if (level >= ZXC_LEVEL_DENSITY) return ZXC_B200_ERROR_UNSUPPORTED;
+    const uint8_t* dict = opts ? (const uint8_t*)opts->dict : NULL;
+    const uint8_t* dict_huf = (opts && opts->dict) ? (const uint8_t*)opts->dict_huf : NULL;
     zxg_ctx* g = zxg_acquire();
     if (!g) return ZXC_ERROR_MEMORY;
     const int64_t r = compress_frame(g, (const uint8_t*)src, src_size, (uint8_t*)dst, dst_capacity, level, block_size,
-                                     checksum, seekable);
+                                     checksum, seekable, dict, dict_size, dict_huf);
     zxg_release(g);
     return r;
 }

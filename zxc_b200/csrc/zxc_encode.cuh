@@ -44,6 +44,8 @@ struct EncodeParams {
     u8* scratch;            /* per warp: tables + stream buffers */
     unsigned long long* counter;
     const u8* dict;         /* dictionary content or NULL */
+    const u32* seed_head;   /* dictionary-seeded head table (ENC_HASH_SIZE entries) or NULL */
+    const unsigned short* seed_chain; /* chain links of the seeded dictionary positions */
     unsigned long long src_size;
     unsigned long long scratch_stride;
     u32 block_size;
@@ -326,6 +328,9 @@ __device__ __forceinline__ void st32(u8* p, u32 v) {
     p[3] = (u8)(v >> 24);
 }
 
+__device__ __forceinline__ void seed_step(const u8* src, u32 i, u32 half, bool hash5, u32* head, unsigned short* chain);
+__device__ __forceinline__ u32 seed_shared_stop(u32 dict_size, bool hash5);
+
 /* one block: zxc_compress_chunk_wrapper (zxc_compress.c:2041-2074) */
 __device__ u32 encode_block(const EncodeParams& P, const u8* blk, u32 n, u8* dst, u8* scratch, u32 lane) {
     const int level = (int)P.level;
@@ -343,16 +348,36 @@ __device__ u32 encode_block(const EncodeParams& P, const u8* blk, u32 n, u8* dst
     unsigned short* offsets = reinterpret_cast<unsigned short*>(seqbuf + ((seq_cap + 3) & ~3u));
     u32* seqwords = reinterpret_cast<u32*>(seqbuf);
 
-    /* fresh tables per block (the reference's epoch bump) */
-    for (u32 k = lane; k < ENC_HASH_SIZE / 4; k += 32) reinterpret_cast<uint4*>(head)[k] = make_uint4(0, 0, 0, 0);
+    const u32 base = P.dict ? P.dict_size : 0u; /* the dictionary is logically prepended to the block */
+    const u8* src = blk; /* block start is 4-byte aligned (block_size multiple of 4096, aligned base) */
+    if (base) {
+        /* tables as zxc_lz_seed_dict leaves them (:1060-1100), cloned instead of re-seeded per block
+         * (output-identical); [dict | block] materialised so positions are contiguous */
+        for (u32 k = lane; k < ENC_HASH_SIZE / 4; k += 32)
+            reinterpret_cast<uint4*>(head)[k] = reinterpret_cast<const uint4*>(P.seed_head)[k];
+        const u32 nchain = min(base, ENC_WINDOW);
+        for (u32 k = lane; k < nchain; k += 32) chain[k] = P.seed_chain[k];
+        u8* comb = extras + bs / 4 + 64;
+        for (u32 k = lane; k < base; k += 32) comb[k] = P.dict[k];
+        for (u32 k = lane; k < n; k += 32) comb[base + k] = blk[k];
+        for (u32 k = lane; k < 16; k += 32) comb[base + n + k] = 0;
+        src = comb;
+        __syncwarp();
+        if (base >= 5 && lane == 0) { /* positions whose hash window reaches into the block */
+            const bool h5 = level >= 3;
+            for (u32 i = seed_shared_stop(base, h5); i < base - 4; i++) seed_step(src, i, (base - 4) / 2, h5, head, chain);
+        }
+    } else {
+        /* fresh tables per block (the reference's epoch bump) */
+        for (u32 k = lane; k < ENC_HASH_SIZE / 4; k += 32) reinterpret_cast<uint4*>(head)[k] = make_uint4(0, 0, 0, 0);
+    }
     __syncwarp();
 
-    const u8* src = blk; /* block start is 4-byte aligned (block_size multiple of 4096, aligned base) */
-    const u32 iend = n;
-    u32 ip = 0, anchor = 0;
+    const u32 iend = base + n;
+    u32 ip = base, anchor = base;
     u32 seq_c = 0, lit_c = 0, ext_c = 0, max_off = 0;
 
-    if (n > 8) {
+    if (n + base > 8 && iend - 8 > base) {
         const u32 search_limit = iend - 8;
         while (ip < search_limit) {
             const u32 dist = ip - anchor;
@@ -515,6 +540,36 @@ __global__ void __launch_bounds__(ENC_CTA_THREADS) zxc_encode_kernel(const Encod
         __syncwarp();
         if (lane == 0) P.out_size[j] = w;
     }
+}
+
+/* zxc_lz_seed_dict (zxc_compress.c:1060-1100): sparse first half (every 4th position, chain link
+ * 0), dense second half with chain links.  Sequential by nature; runs once per call on one thread. */
+__device__ __forceinline__ void seed_step(const u8* src, u32 i, u32 half, bool hash5, u32* head, unsigned short* chain) {
+    if (i < half) {
+        if ((i & 3u) == 0) {
+            head[enc_hash(ldu64(src, i), hash5)] = i;
+            chain[i & (ENC_WINDOW - 1)] = 0;
+        }
+    } else {
+        const u32 h = enc_hash(ldu64(src, i), hash5);
+        const u32 prev = head[h];
+        head[h] = i;
+        chain[i & (ENC_WINDOW - 1)] = (prev != 0 && i - prev < ENC_WINDOW) ? (unsigned short)(i - prev) : 0;
+    }
+}
+/* The 4-byte hash of levels 1-2 mixes 6 input bytes, so the last seeded position reads the first
+ * byte of the BLOCK; that one position is seeded per block (encode_block), the rest here. */
+__device__ __forceinline__ u32 seed_shared_stop(u32 dict_size, bool hash5) {
+    const u32 limit = dict_size - 4;
+    return hash5 ? limit : limit - 1;
+}
+__global__ void zxc_seed_kernel(const u8* dict, u32 dict_size, u32 level, u32* head, unsigned short* chain) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (dict_size < 5) return;
+    const bool hash5 = level >= 3;
+    const u32 half = (dict_size - 4) / 2;
+    const u32 stop = seed_shared_stop(dict_size, hash5);
+    for (u32 i = 0; i < stop; i++) seed_step(dict, i, half, hash5, head, chain);
 }
 
 /* gather the per-block slots into the contiguous frame body */

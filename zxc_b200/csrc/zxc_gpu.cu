@@ -463,7 +463,7 @@ static u32 enc_staging_stride(u32 bs) { return ((bs + 8u + 68u + 4u) + 255u) & ~
 static size_t enc_scratch_stride(u32 bs) {
     const size_t seq_cap = bs / 5 + 32;
     size_t n = (size_t)ENC_HASH_SIZE * 4 + (size_t)ENC_WINDOW * 2 + (((size_t)bs + 63) & ~(size_t)63) + 64 +
-               seq_cap * 4 + bs / 4 + 64;
+               seq_cap * 4 + bs / 4 + 64 + /* [dict | block] */ 65536 + bs + 64;
     return (n + 255) & ~(size_t)255;
 }
 
@@ -472,7 +472,7 @@ static size_t enc_scratch_stride(u32 bs) {
  * not fit body_cap (then *body_size holds the size that would have been needed). */
 extern "C" int zxg_encode_body(zxg_ctx* c, const uint8_t* h_src, uint64_t src_size, uint32_t block_size, int level,
                                int checksum, uint32_t n_blocks, uint8_t* h_body, uint64_t body_cap,
-                               uint32_t* h_sizes, uint64_t* body_size) {
+                               uint32_t* h_sizes, uint64_t* body_size, const void* h_dict, uint32_t dict_size) {
     *body_size = 0;
     if (n_blocks == 0) return ZXC_OK;
     const u32 sstride = enc_staging_stride(block_size);
@@ -496,6 +496,23 @@ extern "C" int zxg_encode_body(zxg_ctx* c, const uint8_t* h_src, uint64_t src_si
     P.scratch = d_scratch;
     P.counter = c->counter;
     P.dict = NULL;
+    P.seed_head = NULL;
+    P.seed_chain = NULL;
+    if (h_dict && dict_size) {
+        /* dictionary + its seeded tables: [dict (padded)] [head 128 KB] [chain 128 KB] */
+        const size_t dpad = ((size_t)dict_size + 16 + 255) & ~(size_t)255;
+        u8* d_dict = (u8*)zxg_buffer(c, ZXG_BUF_DICT, dpad + (size_t)ENC_HASH_SIZE * 4 + (size_t)ENC_WINDOW * 2);
+        if (!d_dict) return ZXC_ERROR_MEMORY;
+        if (cudaMemsetAsync(d_dict, 0, dpad + (size_t)ENC_HASH_SIZE * 4 + (size_t)ENC_WINDOW * 2, c->stream) != cudaSuccess)
+            return ZXC_B200_ERROR_CUDA;
+        rc = zxg_h2d(c, d_dict, h_dict, dict_size);
+        if (rc != ZXC_OK) return rc;
+        P.dict = d_dict;
+        P.seed_head = (const u32*)(d_dict + dpad);
+        P.seed_chain = (const unsigned short*)(d_dict + dpad + (size_t)ENC_HASH_SIZE * 4);
+        zxc_seed_kernel<<<1, 32, 0, c->stream>>>(d_dict, dict_size, (u32)level, (u32*)P.seed_head, (unsigned short*)P.seed_chain);
+        __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
+    }
     P.src_size = src_size;
     P.scratch_stride = wstride;
     P.block_size = block_size;
@@ -503,7 +520,7 @@ extern "C" int zxg_encode_body(zxg_ctx* c, const uint8_t* h_src, uint64_t src_si
     P.staging_stride = sstride;
     P.level = (u32)level;
     P.checksum = checksum ? 1u : 0u;
-    P.dict_size = 0;
+    P.dict_size = P.dict ? dict_size : 0;
     if (cudaMemsetAsync(c->counter, 0, sizeof(unsigned long long), c->stream) != cudaSuccess) return ZXC_B200_ERROR_CUDA;
     zxc_encode_kernel<<<grid, ENC_CTA_THREADS, 0, c->stream>>>(P);
     __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
