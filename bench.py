@@ -354,6 +354,24 @@ def main():
             line["cpu_baseline"] = {"value": round(mt, 3), "unit": "GB/s", "cores": threads, "kind": "reference",
                                     "sample": f"whole {args.gib:g} GiB frame, zxc_seekable_decompress_range_mt best of {reps}",
                                     "single_thread_gbs": round(st, 3)}
+            # ---- supplementary: the encoder (BASELINE.json configs[2] shape at the level this build
+            # covers): 1 GiB, level 3, through zxc_compress with host buffers; frame must be byte-identical
+            enc_n = min(n, 1 << 30)
+            src_v = data[:enc_n]
+            cap = int(prod.lib.zxc_compress_bound(enc_n))
+            enc_out = np.zeros(cap, dtype=np.uint8)
+            o = z.CompressOpts(level=LEVEL, block_size=BLOCK, seekable=1)
+            r_enc = prod.lib.zxc_compress(src_v.ctypes.data, enc_n, enc_out.ctypes.data, cap, C.byref(o))  # warm-up
+            t = time.perf_counter()
+            r_enc = prod.lib.zxc_compress(src_v.ctypes.data, enc_n, enc_out.ctypes.data, cap, C.byref(o))
+            enc_dt = time.perf_counter() - t
+            t = time.perf_counter()
+            ref_frame = zc.compress_ref_mt(ref, src_v, level=LEVEL, block_size=BLOCK)
+            ref_dt = time.perf_counter() - t
+            line["encode"] = {"level": LEVEL, "bytes_in": int(enc_n), "gbs_in_e2e": round(enc_n / enc_dt / 1e9, 3),
+                              "identical_to_reference": bool(r_enc == ref_frame.size and np.array_equal(enc_out[:r_enc], ref_frame)),
+                              "cpu_reference_gbs_in": round(enc_n / ref_dt / 1e9, 3), "cpu_threads": threads,
+                              "note": "levels 1-5 are on the GPU; level 6 (configs[2]) needs the optimal parser + PivCo stage"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

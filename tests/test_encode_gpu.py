@@ -110,3 +110,28 @@ def test_dictionary_frames_identical_to_reference(prod, ref):
     fr = prod.compress(payload, level=3, dict=GC_DICT)
     want = [l.split()[0] for l in open(os.path.join(G, "format", "golden.sha256")) if "09_block_dict" in l][0]
     assert hashlib.sha256(fr.tobytes()).hexdigest() == want
+
+
+def test_block_api_compress_identical(prod, ref):
+    import ctypes as C
+    data = zc.silesia_shaped(4 << 20, seed=77)
+    rc_ref = ref.lib.zxc_create_cctx(None)
+    rc_prod = prod.lib.zxc_create_cctx(None)
+    dctx = prod.lib.zxc_create_dctx()
+    for n, level, cks in ((4096, 5, 0), (65536, 3, 1), (100000, 1, 0), (700, 3, 1), (1 << 20, 4, 0), (9, 3, 0), (1, 2, 1)):
+        src = data[1000:1000 + n].copy()
+        cap = int(ref.lib.zxc_compress_block_bound(n))
+        a = np.zeros(cap, np.uint8)
+        b = np.zeros(cap, np.uint8)
+        o = z.CompressOpts(level=level, checksum_enabled=cks)
+        ra = ref.lib.zxc_compress_block(rc_ref, src.ctypes.data, n, a.ctypes.data, cap, C.byref(o))
+        rb = prod.lib.zxc_compress_block(rc_prod, src.ctypes.data, n, b.ctypes.data, cap, C.byref(o))
+        assert ra == rb > 0, (n, level, ra, rb)
+        assert np.array_equal(a[:ra], b[:rb]), (n, level)
+        out = np.zeros(n, np.uint8)
+        do = z.DecompressOpts(checksum_enabled=cks)
+        assert prod.lib.zxc_decompress_block(dctx, b.ctypes.data, rb, out.ctypes.data, n, C.byref(do)) == n
+        assert np.array_equal(out, src)
+    prod.lib.zxc_free_cctx(rc_prod)
+    ref.lib.zxc_free_cctx(rc_ref)
+    prod.lib.zxc_free_dctx(dctx)

@@ -631,12 +631,27 @@ int64_t zxc_compress_cctx(zxc_cctx* cctx, const void* src, size_t src_size, void
 
 int64_t zxc_compress_block(zxc_cctx* cctx, const void* src, size_t src_size, void* dst, size_t dst_capacity,
                            const zxc_compress_opts_t* opts) {
-    (void)opts;
     if (!cctx || !src || !dst || src_size == 0 || dst_capacity == 0) return ZXC_ERROR_NULL_INPUT;
     if (src_size > ZXC_BLOCK_SIZE_MAX) return ZXC_ERROR_BAD_BLOCK_SIZE;
+    const int checksum = opts ? opts->checksum_enabled : cctx->checksum;
+    const int level = level_clamp((opts && opts->level > 0) ? opts->level : cctx->level);
+    const uint8_t* dict = opts ? (const uint8_t*)opts->dict : NULL;
+    const size_t dict_size = (opts && opts->dict) ? opts->dict_size : 0;
+    if (dict_size > ZXC_DICT_SIZE_MAX) return ZXC_ERROR_DICT_TOO_LARGE;
     const int irc = zxg_init();
     if (irc != ZXC_OK) return irc;
-    return ZXC_B200_ERROR_UNSUPPORTED;
+    if (level >= ZXC_LEVEL_DENSITY) return ZXC_B200_ERROR_UNSUPPORTED;
+    cctx->level = level; /* sticky, like the reference (zxc_dispatch.c:1667-1669) */
+    cctx->checksum = checksum;
+    if (!cctx->gpu) cctx->gpu = zxg_create();
+    if (!cctx->gpu) return ZXC_ERROR_MEMORY;
+    uint32_t size = 0;
+    uint64_t body = 0;
+    /* one frameless block: the same kernel with a single job */
+    const int rc = zxg_encode_body(cctx->gpu, (const uint8_t*)src, src_size, (uint32_t)zxf_block_size_ceil(src_size),
+                                   level, checksum, 1, (uint8_t*)dst, dst_capacity, &size, &body, dict,
+                                   (uint32_t)dict_size);
+    return rc != ZXC_OK ? rc : (int64_t)body;
 }
 
 /* ------------------------------------------------------------------------- */
