@@ -30,9 +30,6 @@ def test_conformance_valid(prod, orc, name):
     did = int.from_bytes(frame[7:11], "little") if frame[6] & 0x40 else 0
     d, h = golden_dicts().get(did, (None, None))
     r, out = prod.decompress(frame, len(exp), checksum=1, dict=d, dict_huf=h)  # exact-size dst
-    if frame_uses_huffman(orc, frame) or name in ("glo_pivco_wide_l7", "dict_seekable_l7"):
-        if r == -102:
-            pytest.xfail("PivCo Huffman sections not on the GPU yet (SURVEY 8(f)-1)")
     assert r == len(exp), z.ERR.get(r, r)
     assert out.tobytes() == exp
 
@@ -54,17 +51,15 @@ def test_golden_format_frames(prod, orc):
         n = prod.lib.zxc_get_decompressed_size(frame, len(frame))
         d = GC_DICT if frame[6] & 0x40 else None
         if os.path.basename(p).startswith("12_"):
-            continue  # needs the trained shared table; covered once Huffman lands
+            continue  # needs the reference trainer's shared table (zxc_train_dict_huf), not a fixture
         r0, o0 = orc.decompress(frame, n, checksum=1, dict=d)
         r1, o1 = prod.decompress(frame, n, checksum=1, dict=d)
-        if r1 == -102 and frame_uses_huffman(orc, frame):
-            continue
         assert r0 == r1 == n, (p, r0, r1)
         assert np.array_equal(o0, o1), p
 
 
 @pytest.mark.parametrize("kind,n", CASES)
-@pytest.mark.parametrize("level", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("level", [1, 2, 3, 4, 5, 6, 7])
 def test_differential_vs_reference(prod, ref, kind, n, level):
     data = make_case(kind, n)
     for bs, cks, seek in ((4096, 1, 0), (65536, 0, 1), (0, 0, 0), (2 << 20, 1, 1)):
@@ -239,3 +234,29 @@ def test_pinned_pipelined_frame_path(prod, ref):
     f2[int(f2.numel() * 0.9)] ^= 0x10
     r0, _ = ref.decompress(f2.numpy(), n, checksum=1)
     assert prod.lib.zxc_decompress(f2.data_ptr(), f2.numel(), h_out.data_ptr(), n, C.byref(o)) == r0 < 0
+
+
+def test_huffman_sections(prod, ref, orc):
+    """PivCo literal (level 6+) and token (level 7) sections, incl. the shared dictionary table."""
+    import ctypes as C
+    data = zc.silesia_shaped(6 << 20, seed=51, offset=120 << 20)
+    for level, bs in ((6, 65536), (7, 65536), (6, 4096), (7, 1 << 20)):
+        frame = zc.compress_ref_mt(ref, data, level=level, block_size=bs, checksum=1)
+        rc, st = orc.stats(frame)
+        assert st["huf_blocks"] > 0
+        r, out = prod.decompress(frame, data.size, checksum=1)
+        assert r == data.size, z.ERR.get(r, r)
+        assert np.array_equal(out, data)
+    # mutation parity on a Huffman frame
+    small = data[:150000]
+    frame = ref.compress(small, level=7, block_size=65536, checksum=0)
+    rng = np.random.default_rng(5)
+    for t in range(80):
+        f = frame.copy()
+        pos = int(rng.integers(16, f.size - 12))
+        f[pos] ^= int(rng.integers(1, 256))
+        r0, o0 = ref.decompress(f, small.size)
+        r1, o1 = prod.decompress(f, small.size)
+        assert (r0 < 0) == (r1 < 0), (t, pos, r0, r1)
+        if r0 >= 0:
+            assert r0 == r1 and np.array_equal(o0, o1)

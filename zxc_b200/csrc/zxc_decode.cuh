@@ -58,6 +58,7 @@ struct DecodeParams {
     u32 dict_size;
     u32 scratch_stride;
     u32 flags;
+    u32 block_cap; /* largest decoded block size of this launch: sizes the per-warp scratch regions */
 };
 
 /* ------------------------------------------------------------------------- */
@@ -76,6 +77,16 @@ __device__ __forceinline__ u32 warp_incl_scan(u32 v, u32 lane) {
         if (lane >= (u32)d) v += t;
     }
     return v;
+}
+
+#include "zxc_huffman.cuh"
+
+/* per-warp scratch layout (bytes), a function of the launch's block_cap */
+__host__ __device__ __forceinline__ u32 scr_lit_cap(u32 bs) { return (bs + 255u) & ~255u; }
+__host__ __device__ __forceinline__ u32 scr_tok_cap(u32 bs) { return (bs / 4u + 64u + 255u) & ~255u; }
+__host__ __device__ __forceinline__ u32 scr_cum_cap(u32 bs) { return (bs + 4096u + 255u) & ~255u; }
+__host__ __device__ __forceinline__ u32 scr_stride(u32 bs) {
+    return 256u + scr_lit_cap(bs) + scr_tok_cap(bs) + (u32)HUF_WORK_BYTES + scr_cum_cap(bs);
 }
 
 /* warp-wide byte copy, global -> global, non-overlapping */
@@ -220,7 +231,12 @@ struct Sections {
 };
 
 __device__ int parse_sections(const u8* pay, u32 comp, bool ghi, u32 cap, const u8* dict_huf, u8* scratch,
-                              u32 scratch_cap, u32 lane, Sections& S) {
+                              u32 block_cap, u32 lane, Sections& S) {
+    /* scratch points at this warp's literal buffer; token buffer, Huffman work area follow */
+    const u32 scratch_cap = scr_lit_cap(block_cap);
+    u8* tok_buf = scratch + scratch_cap;
+    HufWork* hw = reinterpret_cast<HufWork*>(tok_buf + scr_tok_cap(block_cap));
+    u32* cum = reinterpret_cast<u32*>(reinterpret_cast<u8*>(hw) + HUF_WORK_BYTES);
     if (comp < 12) return ZXC_ERROR_BAD_HEADER;
     const u32 n_seq = ld32(pay), n_lit = ld32(pay + 4);
     const u32 enc_lit = pay[8], enc_tok = pay[9], enc_off = pay[11];
@@ -245,10 +261,22 @@ __device__ int parse_sections(const u8* pay, u32 comp, bool ghi, u32 cap, const 
             if (n_lit != 0) {
                 if (n_lit > cap) return ZXC_ERROR_DST_TOO_SMALL;
                 if (enc_lit == 3 && !dict_huf) return ZXC_ERROR_DICT_REQUIRED;
-                return ZXC_B200_ERROR_UNSUPPORTED; /* PivCo literal sections: SURVEY 8(f)-1 */
+                if (n_lit > scratch_cap) return ZXC_ERROR_CORRUPT_DATA; /* lit_buffer_cap, :774 */
+                int rc;
+                if (enc_lit == 2) {
+                    if (lit_comp < 128) return ZXC_ERROR_CORRUPT_DATA;
+                    rc = pivco_decode(p_data, p_data + 128, lit_comp - 128, scratch, n_lit, hw, cum, lane);
+                } else {
+                    rc = pivco_decode(dict_huf, p_data, lit_comp, scratch, n_lit, hw, cum, lane);
+                }
+                if (rc != ZXC_OK) return rc;
+                __syncwarp();
+                S.lit = scratch;
+                S.n_lit_avail = n_lit;
+            } else {
+                S.lit = p_data;
+                S.n_lit_avail = 0;
             }
-            S.lit = p_data;
-            S.n_lit_avail = 0;
         } else if (enc_lit == 1) {
             if (n_lit > 0) {
                 if (n_lit > cap) return ZXC_ERROR_DST_TOO_SMALL;
@@ -273,10 +301,18 @@ __device__ int parse_sections(const u8* pay, u32 comp, bool ghi, u32 cap, const 
         const u64 consumed = (u64)lit_comp + tok_comp + sz_off;
         if (consumed > avail) return ZXC_ERROR_CORRUPT_DATA;
         if (avail - lit_comp < 32) return ZXC_ERROR_CORRUPT_DATA;
-        if (enc_tok == 2) return ZXC_B200_ERROR_UNSUPPORTED; /* PivCo token sections: 8(f)-1 */
-        if (enc_tok != 0) return ZXC_ERROR_CORRUPT_DATA;
+        if (enc_tok != 0 && enc_tok != 2) return ZXC_ERROR_CORRUPT_DATA;
         S.tok = p_data + lit_comp;
         S.offs = S.tok + tok_comp;
+        if (enc_tok == 2) { /* level 7: Huffman-coded tokens (:1019-1022) */
+            if (n_seq + 32u > scr_tok_cap(block_cap) || tok_comp < 128) return ZXC_ERROR_CORRUPT_DATA;
+            if (n_seq) {
+                const int rc = pivco_decode(S.tok, S.tok + 128, tok_comp - 128, tok_buf, n_seq, hw, cum, lane);
+                if (rc != ZXC_OK) return rc;
+                __syncwarp();
+            }
+            S.tok = tok_buf;
+        }
         S.ext = S.offs + (u32)sz_off;
         S.ext_end = avail - (u32)consumed;
     } else {
@@ -729,7 +765,7 @@ __device__ int decode_job(const DecodeParams& P, const zxc_b200_job_t& job, u8* 
         case BT_GLO:
         case BT_GHI:
             return decode_lz_block(data, comp, type == BT_GHI, out, job.dst_cap, P.dict, P.dict_size,
-                                   P.dict_huf, scratch, P.scratch_stride - 256u, ring, lane);
+                                   P.dict_huf, scratch, P.block_cap, ring, lane);
         case BT_RAW:
             if (comp > job.dst_cap) return ZXC_ERROR_DST_TOO_SMALL;
             warp_copy(out, data, comp, lane);

@@ -257,7 +257,7 @@ static int grid_for(u32 n_jobs) {
 }
 
 /* per-warp scratch for expanded literal sections; 256 bytes of lead-in so word loads may start below it */
-static u32 scratch_stride_for(u32 block_size) { return ((block_size + 255u) & ~255u) + 256u; }
+static u32 scratch_stride_for(u32 block_size) { return scr_stride(block_size); }
 
 extern "C" size_t zxc_b200_decode_scratch_size(uint32_t block_size) {
     if (zxg_init() != ZXC_OK) return 0;
@@ -283,6 +283,7 @@ static int launch_decode(const void* d_src, void* d_dst, const zxc_b200_job_t* d
     P.dict_size = d_dict ? dict_size : 0;
     P.scratch_stride = scratch_stride_for(block_size);
     P.flags = verify ? FLAG_VERIFY : 0;
+    P.block_cap = block_size;
     const int grid = grid_for(n_jobs);
     if ((size_t)grid * WARPS_PER_CTA * P.scratch_stride > scratch_size) return ZXC_ERROR_MEMORY;
     if (cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st) != cudaSuccess) return ZXC_B200_ERROR_CUDA;
