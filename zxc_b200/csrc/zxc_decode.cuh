@@ -133,6 +133,14 @@ __device__ __forceinline__ u32 read_varint(const u8* e, u32& pos, u32 end) {
     return 0;
 }
 
+/* cursor after one varint, advancing exactly as read_varint would */
+__device__ __forceinline__ u32 varint_advance(const u8* e, u32 pos, u32 end) {
+    if (pos >= end) return pos;
+    const u32 b0 = e[pos];
+    const u32 nxt = pos + 1u + (b0 >> 7) + ((b0 & 0xC0u) == 0xC0u);
+    return (b0 >= 0xE0u || nxt > end) ? end : nxt;
+}
+
 /* ------------------------------------------------------------------------- */
 /* rapidhash V3 folded to 32 bits, warp-cooperative (vendors/rapidhash.h).    */
 /* Lanes 0..6 own the seven stripe accumulators; the tail is warp-uniform.    */
@@ -575,36 +583,34 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
         const bool valid = i < n_seq;
         u32 ll = 0, ml = 0, off = 1;
         if (valid) {
+            u32 a, b = 0;
             if (!ghi) {
-                const u32 t = tok[i];
-                ll = t >> 4;
-                ml = t & 15;
-                off = (enc_off ? (u32)offs[i] : ld16(offs + 2 * (size_t)i)) + 1;
+                a = tok[i];
+                b = enc_off ? (u32)offs[i] : ld16(offs + 2 * (size_t)i);
             } else {
-                const u32 wd = ld32(tok + 4 * (size_t)i);
-                ll = wd >> 24;
-                ml = (wd >> 16) & 0xFF;
-                off = (wd & 0xFFFF) + 1;
+                a = ld32(tok + 4 * (size_t)i);
+            }
+            if (!ghi) {
+                ll = a >> 4;
+                ml = a & 15;
+                off = b + 1;
+            } else {
+                ll = a >> 24;
+                ml = (a >> 16) & 0xFF;
+                off = (a & 0xFFFF) + 1;
             }
         }
         /* ---- escapes: one uniform walk over the batch's varints ---- */
         const bool e_ll = valid && ll == esc, e_ml = valid && ml == esc;
         const u32 m_ll = __ballot_sync(FULL, e_ll), m_ml = __ballot_sync(FULL, e_ml);
-        u32 step_lo = 0, step_hi = 0, k_esc = 0, epos_end = epos;
+        u32 k_esc = 0, epos_end = epos;
         if (m_ll | m_ml) {
             const u32 ord_ll = __popc(m_ll & lt_mask) + __popc(m_ml & lt_mask);
             k_esc = __popc(m_ll) + __popc(m_ml);
             u32 my_pos = ext_end; /* cursor where this lane's first varint starts */
             for (u32 s = 0; s < k_esc; s++) {
-                if (s == lane) step_lo = epos_end;
-                if (s == lane + 32) step_hi = epos_end;
                 if (s == ord_ll) my_pos = epos_end;
-                /* advance exactly as read_varint would (zxc_decompress.c:51-88) */
-                if (epos_end < ext_end) {
-                    const u32 b0 = ext[epos_end];
-                    const u32 len = 1u + (b0 >= 0x80u) + (b0 >= 0xC0u);
-                    epos_end = (b0 >= 0xE0u || epos_end + len > ext_end) ? ext_end : epos_end + len;
-                }
+                epos_end = varint_advance(ext, epos_end, ext_end);
             }
             if (e_ll) ll += read_varint(ext, my_pos, ext_end);
             if (e_ml) ml += read_varint(ext, my_pos, ext_end);
@@ -642,7 +648,7 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
             for (u32 p = ring_lo + lane; p < O; p += 32) ring[p & mask] = out[p];
             __syncwarp();
             const u32 q = ((m_ll & 1u) ? 1u : 0u) + ((m_ml & 1u) ? 1u : 0u);
-            epos = (q == k_esc) ? epos_end : __shfl_sync(FULL, step_lo, q);
+            for (u32 s = 0; s < q; s++) epos = varint_advance(ext, epos, ext_end); /* rare: re-walk */
             base += 1;
             continue;
         }
@@ -731,7 +737,7 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
         if (m < nvalid) {
             const u32 below = (1u << m) - 1u;
             const u32 q = __popc(m_ll & below) + __popc(m_ml & below);
-            epos = (q == k_esc) ? epos_end : (q < 32 ? __shfl_sync(FULL, step_lo, q) : __shfl_sync(FULL, step_hi, q - 32));
+            for (u32 s = 0; s < q; s++) epos = varint_advance(ext, epos, ext_end); /* rare: re-walk */
             base += m;
         } else {
             epos = epos_end;
