@@ -32,6 +32,7 @@
 
 #define ENC_WARPS_PER_CTA 4
 #define ENC_CTA_THREADS (ENC_WARPS_PER_CTA * 32)
+#define ENC_CTAS_PER_SM 8u
 #define ENC_HASH_BITS 15
 #define ENC_HASH_SIZE (1u << ENC_HASH_BITS)
 #define ENC_WINDOW 65536u

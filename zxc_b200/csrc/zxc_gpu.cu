@@ -479,7 +479,7 @@ extern "C" int zxg_encode_body(zxg_ctx* c, const uint8_t* h_src, uint64_t src_si
     const u32 sstride = enc_staging_stride(block_size);
     const size_t wstride = enc_scratch_stride(block_size);
     const u32 ctas_needed = (n_blocks + ENC_WARPS_PER_CTA - 1) / ENC_WARPS_PER_CTA;
-    const u32 resident = (u32)(g_sm_count > 0 ? g_sm_count : 148) * 3u;
+    const u32 resident = (u32)(g_sm_count > 0 ? g_sm_count : 148) * ENC_CTAS_PER_SM;
     const u32 grid = ctas_needed < resident ? ctas_needed : resident;
     u8* d_src = (u8*)zxg_buffer(c, ZXG_BUF_IN, (size_t)src_size + 64);
     u8* d_stage = (u8*)zxg_buffer(c, ZXG_BUF_OUT, (size_t)n_blocks * sstride);
