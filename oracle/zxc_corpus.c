@@ -387,3 +387,52 @@ int zxcorp_fill(uint8_t* dst, uint64_t offset, uint64_t len, uint64_t seed) {
 }
 
 int zxcorp_class_of_chunk(uint64_t chunk) { return unit_class((unsigned)(chunk % UNIT_CHUNKS)); }
+
+/* ------------------------------------------------------------------------- */
+/* config 4 input: fixed-size JSON-ish records from a 200-key  */
+/* schema with Zipf-distributed values; record r is a pure function of (seed,r).*/
+/* ------------------------------------------------------------------------- */
+int zxcorp_records(uint8_t* dst, uint64_t first_record, uint64_t n_records, uint32_t record_size, uint64_t seed) {
+    vocab_init();
+    const vocab_t* v = &g_vocab[0];
+    for (uint64_t r = 0; r < n_records; r++) {
+        rng_t g = {(seed * 0x9E3779B97F4A7C15ull) ^ ((first_record + r) * 0xD1B54A32D192ED03ull) ^ 0x1234ABCDull};
+        if (g.s == 0) g.s = 1;
+        rnd(&g);
+        uint8_t* d = dst + r * record_size;
+        size_t p = 0;
+        p = put(d, p, record_size, "{", 1);
+        int first = 1;
+        while (p + 48 < record_size) {
+            const uint32_t key = zipf(&g, 200);
+            const uint32_t x = (uint32_t)(rnd(&g) >> 32);
+            if (!first) p = put(d, p, record_size, ",", 1);
+            first = 0;
+            p = put(d, p, record_size, "\"", 1);
+            p = put(d, p, record_size, v->w[key * 7 % VOCAB], v->len[key * 7 % VOCAB]);
+            p = put(d, p, record_size, "_", 1);
+            p = put(d, p, record_size, v->w[key], v->len[key]);
+            p = put(d, p, record_size, "\":", 2);
+            switch (key % 4) {
+                case 0: p = put_num(d, p, record_size, zipf(&g, 1000000), 1); break;
+                case 1: {
+                    const uint32_t w = zipf(&g, 512);
+                    p = put(d, p, record_size, "\"", 1);
+                    p = put(d, p, record_size, v->w[w], v->len[w]);
+                    p = put(d, p, record_size, "\"", 1);
+                    break;
+                }
+                case 2: p = put(d, p, record_size, (x & 1) ? "true" : "false", (x & 1) ? 4 : 5); break;
+                default: {
+                    char t[32];
+                    const int L = snprintf(t, sizeof t, "\"2026-%02u-%02uT%02u:%02u:%02uZ\"", 1 + x % 12, 1 + (x >> 4) % 28,
+                                           (x >> 9) % 24, (x >> 14) % 60, (x >> 20) % 60);
+                    p = put(d, p, record_size, t, (size_t)L);
+                }
+            }
+        }
+        p = put(d, p, record_size, "}", 1);
+        while (p < record_size) { d[p] = (p + 1 == record_size) ? '\n' : ' '; p++; }
+    }
+    return 0;
+}

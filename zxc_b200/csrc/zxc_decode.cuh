@@ -684,6 +684,26 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
         const u8* m_sp = near ? ring + si : out + src_lo;
         const bool l_word_ok = (out_start & mask) + ll + 4 <= RING_BYTES;
 
+        /* exact dependencies: a match waits only for the earlier matches of this batch whose
+         * destination [mdst_i, mend_i) intersects its source [src_lo, src_end).  Destinations are
+         * ordered by lane, so the blockers are a lane interval [a, b) found by two binary searches
+         * over the warp (shuffle as the array read). */
+        u32 depmask;
+        {
+            const u32 mend = mdst + ml;
+            u32 lo_a = 0, hi_a = lane, lo_b = 0, hi_b = lane; /* blockers are strictly earlier lanes */
+#pragma unroll
+            for (int it = 0; it < 5; it++) {
+                const u32 mid_a = (lo_a + hi_a) >> 1, mid_b = (lo_b + hi_b) >> 1;
+                const i32 e_a = (i32)__shfl_sync(FULL, mend, mid_a);
+                const i32 d_b = (i32)__shfl_sync(FULL, mdst, mid_b);
+                if (lo_a < hi_a) { if (e_a > src_lo) hi_a = mid_a; else lo_a = mid_a + 1; }   /* first lane with mend > src_lo */
+                if (lo_b < hi_b) { if (d_b < src_end) lo_b = mid_b + 1; else hi_b = mid_b; }   /* first lane with mdst >= src_end */
+            }
+            const u32 below_b = lo_b >= 32 ? 0xFFFFFFFFu : ((1u << lo_b) - 1u);
+            const u32 below_a = lo_a >= 32 ? 0xFFFFFFFFu : ((1u << lo_a) - 1u);
+            depmask = below_b & ~below_a;
+        }
         u32 pending = __ballot_sync(FULL, act);
         bool lit_pass = true;
 #pragma unroll 1
@@ -699,9 +719,7 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
                 lok = l_word_ok && ll <= LIT_SHORT;
                 gok = l_word_ok && ll > LIT_SHORT;
             } else {
-                const int first = __ffs(pending) - 1;
-                const i32 W = (i32)__shfl_sync(FULL, mdst, first);
-                ready = ((pending >> lane) & 1u) && ((int)lane == first || src_end <= W);
+                ready = ((pending >> lane) & 1u) && (pending & depmask) == 0;
                 it_d = mdst;
                 it_n = ml;
                 it_sp = m_sp;
