@@ -579,6 +579,7 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
 
     u32 base = 0;
     while (base < n_seq) {
+        /* ---- unpack tokens and offsets ---- */
         const u32 i = base + lane;
         const bool valid = i < n_seq;
         u32 ll = 0, ml = 0, off = 1;
@@ -615,6 +616,7 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
             if (e_ll) ll += read_varint(ext, my_pos, ext_end);
             if (e_ml) ml += read_varint(ext, my_pos, ext_end);
         }
+        /* ---- prefix sums and fit ---- */
         if (valid) ml += 5;
         const u32 tot = ll + ml;
         const u32 s_ll = warp_incl_scan(ll, lane);
@@ -653,6 +655,7 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
             continue;
         }
 
+        /* ---- validation ---- */
         const bool act = lane < m;
         const bool ovf = act && (lit_start + ll > n_lit_avail || out_start + tot > cap);
         const bool bad = act && (mdst + dict_size < off);
@@ -670,6 +673,7 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
         /* ---- copy passes: pass 0 = every literal run (independent of all matches), then match
          * rounds: a match is ready once its source ends below the lowest pending match destination.
          * One body serves all passes so the hot loop stays inside the instruction cache. ---- */
+        /* ---- classify matches ---- */
         const i32 src_lo = (i32)mdst - (i32)off;
         const i32 src_end = min((i32)mdst, src_lo + (i32)ml);
         /* word copies need: no ring wrap on the destination, and a source that is entirely in the
@@ -684,6 +688,7 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
         const u8* m_sp = near ? ring + si : out + src_lo;
         const bool l_word_ok = (out_start & mask) + ll + 4 <= RING_BYTES;
 
+        /* ---- dependency masks ---- */
         /* exact dependencies: a match waits only for the earlier matches of this batch whose
          * destination [mdst_i, mend_i) intersects its source [src_lo, src_end).  Destinations are
          * ordered by lane, so the blockers are a lane interval [a, b) found by two binary searches
@@ -704,6 +709,7 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
             const u32 below_a = lo_a >= 32 ? 0xFFFFFFFFu : ((1u << lo_a) - 1u);
             depmask = below_b & ~below_a;
         }
+        /* ---- pass loop ---- */
         u32 pending = __ballot_sync(FULL, act);
         bool lit_pass = true;
 #pragma unroll 1
@@ -747,6 +753,7 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
             if (!pending) break;
         }
 
+        /* ---- advance and flush ---- */
         O += T;
         L += TL;
         ring_flush(w, F, O & ~511u, lane, al16);
