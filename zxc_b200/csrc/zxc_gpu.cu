@@ -40,7 +40,43 @@ static int g_sm_count = 0;
 static unsigned long long g_launches = 0;
 static pthread_mutex_t g_pool_mu = PTHREAD_MUTEX_INITIALIZER;
 
-#define PIN_CHUNK ((size_t)16 << 20)
+#define PIN_CHUNK ((size_t)32 << 20)
+
+/* Pageable host buffers are staged through pinned bounce buffers; one thread's memcpy (~10 GB/s)
+ * would be far below PCIe Gen5, so large copies are split over a few helper threads. */
+#define STAGE_THREADS 6
+struct stage_job { void* d; const void* s; size_t n; };
+static void* stage_worker(void* p) {
+    const stage_job* j = (const stage_job*)p;
+    memcpy(j->d, j->s, j->n);
+    return NULL;
+}
+static void parallel_memcpy(void* dst, const void* src, size_t n) {
+    if (n < ((size_t)4 << 20)) {
+        memcpy(dst, src, n);
+        return;
+    }
+    pthread_t th[STAGE_THREADS];
+    stage_job jobs[STAGE_THREADS];
+    const size_t per = ((n / STAGE_THREADS) + 4095) & ~(size_t)4095;
+    int started = 0;
+    size_t off = 0;
+    for (int t = 0; t < STAGE_THREADS && off < n; t++) {
+        const size_t len = (t == STAGE_THREADS - 1 || off + per > n) ? n - off : per;
+        jobs[t].d = (u8*)dst + off;
+        jobs[t].s = (const u8*)src + off;
+        jobs[t].n = len;
+        off += len;
+        if (t == 0) continue; /* the calling thread takes the first slice */
+        if (pthread_create(&th[started], NULL, stage_worker, &jobs[t]) != 0) {
+            memcpy(jobs[t].d, jobs[t].s, jobs[t].n);
+            continue;
+        }
+        started++;
+    }
+    memcpy(jobs[0].d, jobs[0].s, jobs[0].n);
+    for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
+}
 
 struct zxg_ctx {
     cudaStream_t stream;
@@ -203,7 +239,7 @@ extern "C" int zxg_h2d(zxg_ctx* c, void* d_dst, const void* h_src, size_t bytes)
     while (done < bytes) {
         const size_t n = bytes - done < PIN_CHUNK ? bytes - done : PIN_CHUNK;
         cudaEventSynchronize(c->pin_ev[slot]); /* previous use of this bounce buffer */
-        memcpy(c->pin[slot], (const u8*)h_src + done, n);
+        parallel_memcpy(c->pin[slot], (const u8*)h_src + done, n);
         if (cudaMemcpyAsync((u8*)d_dst + done, c->pin[slot], n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
             return ZXC_B200_ERROR_CUDA;
         cudaEventRecord(c->pin_ev[slot], c->stream);
@@ -222,30 +258,22 @@ extern "C" int zxg_d2h(zxg_ctx* c, void* h_dst, const void* d_src, size_t bytes)
     }
     const int rc = ensure_pins(c);
     if (rc != ZXC_OK) return rc;
-    /* two-deep pipeline: while chunk k is copied out of its bounce buffer, chunk k+1 is in flight */
-    size_t issued = 0, drained = 0;
-    size_t len[2] = {0, 0};
-    int slot = 0;
-    while (drained < bytes) {
-        if (issued < bytes && len[slot] == 0) {
-            const size_t n = bytes - issued < PIN_CHUNK ? bytes - issued : PIN_CHUNK;
-            if (cudaMemcpyAsync(c->pin[slot], (const u8*)d_src + issued, n, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+    /* double buffer: while chunk k is copied out of its bounce buffer, chunk k+1 is in flight */
+    const size_t nchunks = (bytes + PIN_CHUNK - 1) / PIN_CHUNK;
+    for (size_t k = 0; k <= nchunks; k++) {
+        if (k < nchunks) { /* issue chunk k into slot k&1 (its previous contents were drained at k-1) */
+            const size_t off = k * PIN_CHUNK;
+            const size_t n = bytes - off < PIN_CHUNK ? bytes - off : PIN_CHUNK;
+            if (cudaMemcpyAsync(c->pin[k & 1], (const u8*)d_src + off, n, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
                 return ZXC_B200_ERROR_CUDA;
-            cudaEventRecord(c->pin_ev[slot], c->stream);
-            len[slot] = n;
-            issued += n;
-            if (issued < bytes && len[slot ^ 1] == 0) {
-                slot ^= 1;
-                continue;
-            }
+            cudaEventRecord(c->pin_ev[k & 1], c->stream);
         }
-        const int ds = (len[slot ^ 1] != 0 && (issued - len[slot] - len[slot ^ 1] == drained)) ? (slot ^ 1) : slot;
-        /* drain the older outstanding chunk */
-        if (cudaEventSynchronize(c->pin_ev[ds]) != cudaSuccess) return ZXC_B200_ERROR_CUDA;
-        memcpy((u8*)h_dst + drained, c->pin[ds], len[ds]);
-        drained += len[ds];
-        len[ds] = 0;
-        slot = ds;
+        if (k > 0) { /* drain chunk k-1 */
+            const size_t off = (k - 1) * PIN_CHUNK;
+            const size_t n = bytes - off < PIN_CHUNK ? bytes - off : PIN_CHUNK;
+            if (cudaEventSynchronize(c->pin_ev[(k - 1) & 1]) != cudaSuccess) return ZXC_B200_ERROR_CUDA;
+            parallel_memcpy((u8*)h_dst + off, c->pin[(k - 1) & 1], n);
+        }
     }
     return ZXC_OK;
 }
