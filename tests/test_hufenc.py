@@ -1,0 +1,100 @@
+"""zxc_b200/csrc/zxc_hufenc.h (package-merge, nudge, PivCo sizing -- the level 6-7 entropy-stage
+decisions the encode kernel makes on the device) compiled as host C and pinned against the
+UNMODIFIED reference's internals (oracle/_ref/libzxc_ref_internals.so; reference
+src/lib/zxc_huffman.c:172-311, :803-945, :1219-1249)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST_SO = os.path.join(ROOT, "oracle", "libzxc_hufenc_host.so")
+REFI_SO = os.path.join(ROOT, "oracle", "_ref", "libzxc_ref_internals.so")
+
+pytestmark = pytest.mark.skipif(not (os.path.exists(HOST_SO) and os.path.exists(REFI_SO)),
+                                reason="oracle/ not built (python -c 'import __graft_entry__ as g; g.build()')")
+
+
+@pytest.fixture(scope="module")
+def libs():
+    h, r = C.CDLL(HOST_SO), C.CDLL(REFI_SO)
+    for lib, pre in ((h, "zxhh"), (r, "zxri")):
+        for name in ("build_code_lengths", "nudge_code_lengths"):
+            f = getattr(lib, f"{pre}_{name}")
+            f.restype = C.c_int
+            f.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        f = getattr(lib, f"{pre}_calc_size")
+        f.restype = C.c_uint64
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    return h, r
+
+
+def histograms():
+    rng = np.random.default_rng(1234)
+    out = []
+    for n_sym in (1, 2, 3, 4, 5, 7, 16, 17, 33, 64, 65, 100, 128, 129, 200, 255, 256):
+        for kind in range(6):
+            f = np.zeros(256, np.uint32)
+            syms = rng.choice(256, n_sym, replace=False)
+            if kind == 0:
+                f[syms] = rng.integers(1, 50, n_sym)
+            elif kind == 1:
+                f[syms] = (rng.pareto(1.2, n_sym) * 40 + 1).astype(np.uint32)
+            elif kind == 2:
+                f[syms] = (2.0 ** rng.uniform(0, 17, n_sym)).astype(np.uint32)
+            elif kind == 3:
+                f[syms] = 1
+            elif kind == 4:
+                f[syms] = np.sort(rng.geometric(0.02, n_sym)).astype(np.uint32)
+            else:
+                f[syms] = (np.arange(n_sym) ** 2 + 1).astype(np.uint32)
+            out.append(f)
+    # text-like and binary-like byte histograms
+    text = rng.choice(np.frombuffer(b"etaoin shrdlucmfwypvbgkqjxz ETAOIN.,;\n0123456789", np.uint8), 40000,
+                      p=None)
+    out.append(np.bincount(text, minlength=256).astype(np.uint32))
+    out.append(np.bincount((rng.normal(128, 20, 60000).clip(0, 255)).astype(np.uint8), minlength=256).astype(np.uint32))
+    out.append(np.bincount((rng.exponential(12, 65536).clip(0, 255)).astype(np.uint8), minlength=256).astype(np.uint32))
+    return out
+
+
+@pytest.mark.parametrize("cap", [8, 9, 11])
+def test_package_merge_matches_reference(libs, cap):
+    h, r = libs
+    for f in histograms():
+        a, b = np.zeros(256, np.uint8), np.zeros(256, np.uint8)
+        ra = h.zxhh_build_code_lengths(f.ctypes.data, a.ctypes.data, cap)
+        rb = r.zxri_build_code_lengths(f.ctypes.data, b.ctypes.data, cap)
+        assert (ra == 0) == (rb == 0)
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("cap", [8, 11])
+def test_nudge_and_size_match_reference(libs, cap):
+    h, r = libs
+    adopted = 0
+    for f in histograms():
+        base = np.zeros(256, np.uint8)
+        assert r.zxri_build_code_lengths(f.ctypes.data, base.ctypes.data, cap) == 0
+        a, b = base.copy(), base.copy()
+        ra = h.zxhh_nudge_code_lengths(f.ctypes.data, a.ctypes.data, cap)
+        rb = r.zxri_nudge_code_lengths(f.ctypes.data, b.ctypes.data, cap)
+        assert ra == rb
+        assert np.array_equal(a, b)
+        adopted += rb
+        for hdr in (0, 1):
+            assert h.zxhh_calc_size(f.ctypes.data, a.ctypes.data, hdr) == r.zxri_calc_size(f.ctypes.data, b.ctypes.data, hdr)
+            assert h.zxhh_calc_size(f.ctypes.data, base.ctypes.data, hdr) == r.zxri_calc_size(f.ctypes.data, base.ctypes.data, hdr)
+    assert adopted > 5  # the comparison exercised the adoption path, not only rejections
+
+
+def test_calc_size_rejects_what_the_reference_rejects(libs):
+    h, r = libs
+    f = np.zeros(256, np.uint32)
+    f[:4] = [5, 3, 2, 1]
+    cl = np.zeros(256, np.uint8)
+    cl[:3] = [1, 2, 2]  # symbol 3 present but uncoded
+    assert h.zxhh_calc_size(f.ctypes.data, cl.ctypes.data, 1) == r.zxri_calc_size(f.ctypes.data, cl.ctypes.data, 1) == 2 ** 64 - 1
+    cl[:4] = [1, 2, 3, 4]  # Kraft-incomplete
+    assert h.zxhh_calc_size(f.ctypes.data, cl.ctypes.data, 1) == r.zxri_calc_size(f.ctypes.data, cl.ctypes.data, 1) == 2 ** 64 - 1

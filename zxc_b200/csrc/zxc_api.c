@@ -25,6 +25,7 @@
 #include "zxc_format.h"
 #include "zxc_frame.h"
 #include "zxc_gpu.h"
+#include "zxc_hufenc.h" /* zxh_geometry: validates a dictionary's shared literal table */
 #include "zxc_seekable.h"
 #include "zxc_stream.h"
 
@@ -564,6 +565,22 @@ static int64_t compress_frame(zxg_ctx* g, const uint8_t* src, size_t src_size, u
     const size_t trailer = ZXF_BLOCK_HDR + ((seekable && nb > 0) ? zxc_seek_table_size(nb) : 0) + ZXC_FILE_FOOTER_SIZE;
     if (dst_capacity < ZXC_FILE_HEADER_SIZE + trailer) return ZXC_ERROR_DST_TOO_SMALL;
     const uint32_t did = (dict && dict_size) ? zxc_dict_id(dict, dict_size, dict_huf) : 0;
+    /* the dictionary's shared literal table (zxc_cctx_attach_dict_huf, zxc_common.c:490-513): an
+     * all-zero table means "none"; a malformed one fails the call */
+    uint8_t huf_lens[256];
+    int have_huf = 0;
+    if (dict_huf) {
+        for (int i = 0; i < ZXC_HUF_TABLE_SIZE; i++) {
+            huf_lens[2 * i] = dict_huf[i] & 15u;
+            huf_lens[2 * i + 1] = dict_huf[i] >> 4;
+            have_huf |= dict_huf[i];
+        }
+        if (have_huf) {
+            zxh_geom_t geom;
+            if (zxh_geometry(huf_lens, &geom) != 0) return ZXC_ERROR_CORRUPT_DATA;
+            have_huf = 1;
+        }
+    }
     int r = zxf_write_file_header(dst, dst_capacity, block_size, checksum, did);
     if (r < 0) return r;
     uint32_t* sizes = nb ? (uint32_t*)malloc((size_t)nb * sizeof *sizes) : NULL;
@@ -571,7 +588,8 @@ static int64_t compress_frame(zxg_ctx* g, const uint8_t* src, size_t src_size, u
     uint64_t body = 0;
     const uint64_t body_cap = dst_capacity - ZXC_FILE_HEADER_SIZE - trailer;
     const int rc = zxg_encode_body(g, src, src_size, (uint32_t)block_size, level, checksum, nb,
-                                   dst + ZXC_FILE_HEADER_SIZE, body_cap, sizes, &body, dict, (uint32_t)dict_size);
+                                   dst + ZXC_FILE_HEADER_SIZE, body_cap, sizes, &body, dict, (uint32_t)dict_size,
+                                   have_huf ? huf_lens : NULL);
     if (rc != ZXC_OK) {
         free(sizes);
         return rc;
@@ -604,9 +622,7 @@ int64_t zxc_compress(const void* src, const size_t src_size, void* dst, const si
     if (!zxf_valid_block_size(block_size)) return ZXC_ERROR_BAD_BLOCK_SIZE;
     const int irc = zxg_init();
     if (irc != ZXC_OK) return irc;
-    /* on the GPU this round: the greedy / lazy parsers of levels 1-5, with or without a dictionary; the
-     * optimal parser + PivCo entropy stage (levels 6-7) are not (no CPU fallback: refuse loudly) */
-    if (level >= ZXC_LEVEL_DENSITY) return ZXC_B200_ERROR_UNSUPPORTED;
+    /* every level encodes on the GPU: greedy / lazy parsers (1-5), optimal parser + PivCo stage (6-7) */
     const uint8_t* dict = opts ? (const uint8_t*)opts->dict : NULL;
     const uint8_t* dict_huf = (opts && opts->dict) ? (const uint8_t*)opts->dict_huf : NULL;
     zxg_ctx* g = zxg_acquire();
@@ -640,7 +656,6 @@ int64_t zxc_compress_block(zxc_cctx* cctx, const void* src, size_t src_size, voi
     if (dict_size > ZXC_DICT_SIZE_MAX) return ZXC_ERROR_DICT_TOO_LARGE;
     const int irc = zxg_init();
     if (irc != ZXC_OK) return irc;
-    if (level >= ZXC_LEVEL_DENSITY) return ZXC_B200_ERROR_UNSUPPORTED;
     cctx->level = level; /* sticky, like the reference (zxc_dispatch.c:1667-1669) */
     cctx->checksum = checksum;
     if (!cctx->gpu) cctx->gpu = zxg_create();
@@ -650,7 +665,7 @@ int64_t zxc_compress_block(zxc_cctx* cctx, const void* src, size_t src_size, voi
     /* one frameless block: the same kernel with a single job */
     const int rc = zxg_encode_body(cctx->gpu, (const uint8_t*)src, src_size, (uint32_t)zxf_block_size_ceil(src_size),
                                    level, checksum, 1, (uint8_t*)dst, dst_capacity, &size, &body, dict,
-                                   (uint32_t)dict_size);
+                                   (uint32_t)dict_size, NULL /* the block API attaches no shared table */);
     return rc != ZXC_OK ? rc : (int64_t)body;
 }
 

@@ -29,6 +29,10 @@
 #include <stdint.h>
 
 #include "zxc_decode.cuh" /* u8/u32, FULL, warp_checksum, ld helpers */
+#include "zxc_hufenc.h"
+
+#define ENC_HUFWORK_BYTES ((sizeof(zxh_work_t) + 255u) & ~(size_t)255u)
+#define ENC_PLAN_BYTES 8192u
 
 #define ENC_WARPS_PER_CTA 4
 #define ENC_CTA_THREADS (ENC_WARPS_PER_CTA * 32)
@@ -55,7 +59,47 @@ struct EncodeParams {
     u32 level;
     u32 checksum;
     u32 dict_size;
+    const u8* dict_huf_lens; /* 256 unpacked code lengths of the dictionary's literal table, or NULL */
 };
+
+/* per-warp scratch layout (bytes from the warp's base) */
+struct EncLayout {
+    size_t literals, seqbuf, extras, comb, dp, ends, work, plan, freq, lens, total;
+    u32 seq_cap;
+};
+__host__ __device__ inline EncLayout enc_layout(u32 bs, int level) {
+    EncLayout L;
+    L.seq_cap = bs / 5 + 32;
+    size_t o = (size_t)ENC_HASH_SIZE * 4 + (size_t)ENC_WINDOW * 2;
+    L.literals = o;
+    o += (((size_t)bs + 63) & ~(size_t)63) + 64;
+    L.seqbuf = o;
+    o += (size_t)L.seq_cap * 4;
+    L.extras = o;
+    o += bs / 4 + 64;
+    L.comb = o; /* [dict | block | 16] when a dictionary is attached */
+    o += 65536 + (size_t)bs + 64;
+    o = (o + 255) & ~(size_t)255;
+    L.dp = L.ends = L.work = L.plan = L.freq = L.lens = 0;
+    if (level >= 6) {
+        L.dp = o; /* u64 per position */
+        o += ((size_t)bs + 1) * 8;
+        o = (o + 255) & ~(size_t)255;
+        L.ends = o;
+        o += (size_t)L.seq_cap * 4;
+        o = (o + 255) & ~(size_t)255;
+        L.work = o; /* zxh_work_t */
+        o += ENC_HUFWORK_BYTES;
+        L.plan = o; /* PivcoPlan */
+        o += ENC_PLAN_BYTES;
+        L.freq = o; /* literal and token histograms */
+        o += 2 * 256 * 4;
+        L.lens = o; /* literal, token and temporary code lengths */
+        o += 3 * 256;
+    }
+    L.total = (o + 255) & ~(size_t)255;
+    return L;
+}
 
 struct LzParams {
     int search_depth, sufficient_len, use_lazy, lazy_attempts, lazy_len_threshold;
@@ -125,7 +169,7 @@ struct Match {
 
 /* zxc_lz77_find_best_match (zxc_compress.c:185-547); every lane computes the same scalars */
 __device__ Match find_best_match(const u8* src, u32 ip, u32 iend, u32 search_limit, u32 anchor, u32* head,
-                                 unsigned short* chain, int level, const LzParams& p, u32 lane) {
+                                 unsigned short* chain, int level, const LzParams& p, u32 lane, u32 last_off = 0) {
     const bool hash5 = level >= 3;
     Match best;
     best.ref = 0;
@@ -153,7 +197,18 @@ __device__ Match find_best_match(const u8* src, u32 ip, u32 iend, u32 search_lim
     __syncwarp();
 
     int attempts = p.search_depth;
-    if (match_idx != 0) {
+    bool rep_final = false;
+    /* repeat-offset probe (:233-254), levels 6-7 only: it wins ties against the chain candidates */
+    if (last_off != 0 && last_off <= ENC_MAX_DIST && last_off <= ip) {
+        const u32 rep = ip - last_off;
+        if (ldu32(src, rep) == cur_val) {
+            best.len = warp_lcp(src, ip, rep, iend, 4, 0xFFFFFFFFu, lane);
+            best.ref = rep;
+            best.found = true;
+            rep_final = best.len >= (u32)p.sufficient_len || ip + best.len >= iend;
+        }
+    }
+    if (match_idx != 0 && !rep_final) {
         if (skip_head) {
             const u32 delta = chain[match_idx & (ENC_WINDOW - 1)];
             match_idx = delta ? match_idx - delta : 0;
@@ -333,18 +388,26 @@ __device__ __forceinline__ void seed_step(const u8* src, u32 i, u32 half, bool h
 __device__ __forceinline__ u32 seed_shared_stop(u32 dict_size, bool hash5);
 
 /* one block: zxc_compress_chunk_wrapper (zxc_compress.c:2041-2074) */
-__device__ u32 encode_block(const EncodeParams& P, const u8* blk, u32 n, u8* dst, u8* scratch, u32 lane) {
+#include "zxc_huffman.cuh" /* HUF_MAXLEN, HUF_KIND_*: the section geometry shared with the decoder */
+#include "zxc_encode_opt.cuh"
+static_assert(sizeof(PivcoPlan) <= ENC_PLAN_BYTES, "PivcoPlan must fit its scratch slot");
+
+/* OPT = levels 6-7 (optimal parser + entropy stage); a separate instantiation keeps the level 1-5
+ * kernel at its own register budget */
+template <bool OPT>
+__device__ u32 encode_block(const EncodeParams& P, const u8* blk, u32 n, u8* dst, u8* scratch, u32* hist, u32 lane) {
     const int level = (int)P.level;
     const LzParams lzp = lz_params(level);
     const bool ghi = level <= 2;
     const u32 bs = P.block_size;
 
+    const EncLayout lay = enc_layout(bs, level);
     u32* head = reinterpret_cast<u32*>(scratch);
     unsigned short* chain = reinterpret_cast<unsigned short*>(scratch + ENC_HASH_SIZE * 4);
-    u8* literals = scratch + ENC_HASH_SIZE * 4 + ENC_WINDOW * 2;
-    const u32 seq_cap = bs / 5 + 32;
-    u8* seqbuf = literals + ((bs + 63) & ~63u) + 64;        /* GLO: tokens then u16 offsets; GHI: u32 words */
-    u8* extras = seqbuf + (size_t)seq_cap * 4;
+    u8* literals = scratch + lay.literals;
+    const u32 seq_cap = lay.seq_cap;
+    u8* seqbuf = scratch + lay.seqbuf;                      /* GLO: tokens then u16 offsets; GHI: u32 words */
+    u8* extras = scratch + lay.extras;
     u8* tokens = seqbuf;
     unsigned short* offsets = reinterpret_cast<unsigned short*>(seqbuf + ((seq_cap + 3) & ~3u));
     u32* seqwords = reinterpret_cast<u32*>(seqbuf);
@@ -358,7 +421,7 @@ __device__ u32 encode_block(const EncodeParams& P, const u8* blk, u32 n, u8* dst
             reinterpret_cast<uint4*>(head)[k] = reinterpret_cast<const uint4*>(P.seed_head)[k];
         const u32 nchain = min(base, ENC_WINDOW);
         for (u32 k = lane; k < nchain; k += 32) chain[k] = P.seed_chain[k];
-        u8* comb = extras + bs / 4 + 64;
+        u8* comb = scratch + lay.comb;
         for (u32 k = lane; k < base; k += 32) comb[k] = P.dict[k];
         for (u32 k = lane; k < n; k += 32) comb[base + k] = blk[k];
         for (u32 k = lane; k < 16; k += 32) comb[base + n + k] = 0;
@@ -378,7 +441,16 @@ __device__ u32 encode_block(const EncodeParams& P, const u8* blk, u32 n, u8* dst
     u32 ip = base, anchor = base;
     u32 seq_c = 0, lit_c = 0, ext_c = 0, max_off = 0;
 
-    if (n + base > 8 && iend - 8 > base) {
+    if constexpr (OPT) {
+        const OptOut R = optimal_parse(src, base, n, head, chain, level, lzp, reinterpret_cast<u64*>(scratch + lay.dp),
+                                       reinterpret_cast<u32*>(scratch + lay.ends), literals, tokens, offsets, extras, hist,
+                                       reinterpret_cast<zxh_work_t*>(scratch + lay.work), scratch + lay.lens + 512, lane);
+        seq_c = R.seq_c;
+        lit_c = R.lit_c;
+        ext_c = R.ext_c;
+        max_off = R.max_off;
+        anchor = iend; /* the parser has already gathered the trailing literals */
+    } else if (n + base > 8 && iend - 8 > base) {
         const u32 search_limit = iend - 8;
         while (ip < search_limit) {
             const u32 dist = ip - anchor;
@@ -443,43 +515,116 @@ __device__ u32 encode_block(const EncodeParams& P, const u8* blk, u32 n, u8* dst
      * block that would expand goes straight to RAW and the slot never overflows. ---- */
     u8* p = dst + 8;
     u32 w;
-    u32 enc_lit = 0, rle_sz = 0;
+    u32 enc_lit = ENC_RAW, enc_tok = ENC_RAW, rle_sz = 0, huf_lit_sz = 0, huf_tok_sz = 0;
+    u32 best_j = lit_c; /* J = size + decode tax (zxc_compress.c:1270-1626) */
     if (!ghi && lit_c > 0) {
         rle_sz = rle_size_of(literals, lit_c);
         const u32 prem = level >= 6 ? 1u : 8u; /* zxc_ss_prem_rle_q8 */
-        if (rle_sz + ((lit_c * prem) >> 8) < lit_c) enc_lit = 1;
+        const u32 j = rle_sz + ((lit_c * prem) >> 8);
+        if (j < best_j) {
+            enc_lit = ENC_RLE;
+            best_j = j;
+        }
     }
+    u32* freq_lit = reinterpret_cast<u32*>(scratch + lay.freq);
+    u32* freq_tok = freq_lit + 256;
+    u8* cl_lit = scratch + lay.lens;
+    u8* cl_tok = cl_lit + 256;
+    PivcoPlan* plan = reinterpret_cast<PivcoPlan*>(scratch + lay.plan);
+    zxh_work_t* hw = reinterpret_cast<zxh_work_t*>(scratch + lay.work);
+    if constexpr (OPT) {
+        const int cap = level >= 7 ? 11 : 8; /* zxc_huf_enc_max_code_len */
+        bool have_hist = false;
+        if (lit_c >= HUF_MIN_LITERALS) {
+            warp_histogram(literals, lit_c, 1, hist, lane);
+            for (u32 k = lane; k < 256; k += 32) freq_lit[k] = hist[k];
+            __syncwarp();
+            have_hist = true;
+            if (build_section_lengths(freq_lit, cl_lit, cap, hw, lane)) {
+                const u32 pay = pivco_plan(freq_lit, cl_lit, plan, lane);
+                if (pay != 0xFFFFFFFFu) {
+                    const u32 j = pay + 128u + ((lit_c * 4u) >> 8); /* zxc_ss_prem_huf_q8 */
+                    if (j < best_j) {
+                        enc_lit = ENC_HUF;
+                        best_j = j;
+                        huf_lit_sz = pay + 128u;
+                    }
+                }
+            }
+        }
+        if (P.dict_huf_lens && lit_c > 0) { /* the dictionary's shared table: same bitstream, no header */
+            if (!have_hist) {
+                warp_histogram(literals, lit_c, 1, hist, lane);
+                for (u32 k = lane; k < 256; k += 32) freq_lit[k] = hist[k];
+                __syncwarp();
+            }
+            const u32 pay = pivco_plan(freq_lit, P.dict_huf_lens, plan, lane);
+            if (pay != 0xFFFFFFFFu && pay + ((lit_c * 4u) >> 8) < best_j) {
+                enc_lit = ENC_HUF_DICT;
+                huf_lit_sz = pay;
+            }
+        }
+        if (level >= 7 && seq_c >= HUF_MIN_LITERALS) {
+            warp_histogram(tokens, seq_c, 1, hist, lane);
+            for (u32 k = lane; k < 256; k += 32) freq_tok[k] = hist[k];
+            __syncwarp();
+            if (build_section_lengths(freq_tok, cl_tok, cap, hw, lane)) {
+                const u32 pay = pivco_plan(freq_tok, cl_tok, plan, lane);
+                if (pay != 0xFFFFFFFFu && pay + 128u + ((seq_c * 4u) >> 8) < seq_c) {
+                    enc_tok = ENC_HUF;
+                    huf_tok_sz = pay + 128u;
+                }
+            }
+        }
+    }
+    const u32 off8 = max_off <= 255 ? 1u : 0u;
+    const u32 sz_lit = enc_lit == ENC_RLE ? rle_sz : (enc_lit >= ENC_HUF ? huf_lit_sz : lit_c);
+    const u32 sz_tok = enc_tok == ENC_HUF ? huf_tok_sz : seq_c;
+    const u32 sz_off = off8 ? seq_c : seq_c * 2;
+    const u32 desc = (enc_lit != ENC_RAW ? 4u : 0u) + (enc_tok == ENC_HUF ? 4u : 0u);
     {
-        const u32 off8 = max_off <= 255 ? 1u : 0u;
-        const u32 behind = ghi ? seq_c * 4 + ext_c : seq_c + (off8 ? seq_c : seq_c * 2) + ext_c;
+        const u32 behind = ghi ? seq_c * 4 + ext_c : sz_tok + sz_off + ext_c;
         const u32 pad = behind < 32 ? 32 - behind : 0;
-        const u32 lit_sz = enc_lit ? rle_sz + 4 : lit_c;
-        w = 8 + 12 + lit_sz + behind + pad;
+        w = 8 + 12 + (ghi ? lit_c : desc + sz_lit) + behind + pad;
     }
     if (w >= n) {
         /* expansion: store RAW (:2055-2058) */
     } else if (!ghi) {
-        const u32 off8 = max_off <= 255 ? 1u : 0u;
-        const u32 sz_lit = enc_lit ? rle_sz : lit_c;
-        const u32 sz_off = off8 ? seq_c : seq_c * 2;
         if (lane == 0) {
             st32(p, seq_c);
             st32(p + 4, lit_c);
             p[8] = (u8)enc_lit;
-            p[9] = 0;
+            p[9] = (u8)enc_tok;
             p[10] = 0;
             p[11] = (u8)off8;
-            if (enc_lit) st32(p + 12, sz_lit);
+            u8* dsc = p + 12;
+            if (enc_lit != ENC_RAW) {
+                st32(dsc, sz_lit);
+                dsc += 4;
+            }
+            if (enc_tok == ENC_HUF) st32(dsc, sz_tok);
         }
-        u8* q = p + 12 + (enc_lit ? 4 : 0);
-        if (enc_lit) {
+        __syncwarp();
+        u8* q = p + 12 + desc;
+        if (enc_lit == ENC_RLE) {
             if (lane == 0) rle_write(literals, lit_c, q);
+        } else if (OPT && enc_lit == ENC_HUF) {
+            (void)pivco_plan(freq_lit, cl_lit, plan, lane);
+            (void)pivco_write(literals, lit_c, cl_lit, plan, q, true, lane);
+        } else if (OPT && enc_lit == ENC_HUF_DICT) {
+            (void)pivco_plan(freq_lit, P.dict_huf_lens, plan, lane);
+            (void)pivco_write(literals, lit_c, P.dict_huf_lens, plan, q, false, lane);
         } else {
             warp_bytes(q, literals, lit_c, lane);
         }
         q += sz_lit;
-        warp_bytes(q, tokens, seq_c, lane);
-        q += seq_c;
+        if (OPT && enc_tok == ENC_HUF) {
+            (void)pivco_plan(freq_tok, cl_tok, plan, lane);
+            (void)pivco_write(tokens, seq_c, cl_tok, plan, q, true, lane);
+        } else {
+            warp_bytes(q, tokens, seq_c, lane);
+        }
+        q += sz_tok;
         if (off8) {
             for (u32 k = lane; k < seq_c; k += 32) q[k] = (u8)offsets[k];
         } else {
@@ -488,7 +633,7 @@ __device__ u32 encode_block(const EncodeParams& P, const u8* blk, u32 n, u8* dst
         q += sz_off;
         warp_bytes(q, extras, ext_c, lane);
         q += ext_c;
-        const u32 behind = seq_c + sz_off + ext_c;
+        const u32 behind = sz_tok + sz_off + ext_c;
         const u32 pad = behind < 32 ? 32 - behind : 0;
         if (lane < pad) q[lane] = 0;
     } else {
@@ -525,9 +670,12 @@ __device__ u32 encode_block(const EncodeParams& P, const u8* blk, u32 n, u8* dst
     return w;
 }
 
+template <bool OPT>
 __global__ void __launch_bounds__(ENC_CTA_THREADS) zxc_encode_kernel(const EncodeParams P) {
     const u32 lane = threadIdx.x & 31;
     const u32 gwarp = blockIdx.x * ENC_WARPS_PER_CTA + (threadIdx.x >> 5);
+    __shared__ u32 s_hist[OPT ? ENC_WARPS_PER_CTA : 1][256];
+    u32* hist = s_hist[OPT ? (threadIdx.x >> 5) : 0];
     u8* scratch = P.scratch + (size_t)gwarp * P.scratch_stride;
     for (;;) {
         unsigned long long j = 0;
@@ -537,7 +685,7 @@ __global__ void __launch_bounds__(ENC_CTA_THREADS) zxc_encode_kernel(const Encod
         const unsigned long long off = j * (unsigned long long)P.block_size;
         const unsigned long long rem = P.src_size - off;
         const u32 n = rem < P.block_size ? (u32)rem : P.block_size;
-        const u32 w = encode_block(P, P.src + off, n, P.staging + (size_t)j * P.staging_stride, scratch, lane);
+        const u32 w = encode_block<OPT>(P, P.src + off, n, P.staging + (size_t)j * P.staging_stride, scratch, hist, lane);
         __syncwarp();
         if (lane == 0) P.out_size[j] = w;
     }

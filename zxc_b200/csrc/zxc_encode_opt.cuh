@@ -1,0 +1,451 @@
+/*
+ * zxc_encode_opt.cuh -- levels 6-7 of the sm_100a block encoder (device code only): the price-based
+ * optimal parser and the PivCo (Huffman) section writer, bit-identical to the reference's output.
+ *
+ * Replicated behaviour:
+ *   literal price         zxc_opt_estimate_lit_bits         src/lib/zxc_compress.c:720-749
+ *   forward DP + emission zxc_lz77_optimal_parse_glo        src/lib/zxc_compress.c:795-1042
+ *   section choice        zxc_encode_block_glo              src/lib/zxc_compress.c:1536-1626
+ *   PivCo section bytes   zxc_pivco_encode_core             src/lib/zxc_huffman.c:1257-1342
+ *   code lengths          zxc_hufenc.h (package-merge + nudge; also compiled and pinned on the host)
+ *
+ * Mechanism (one warp per block, as for levels 1-5):
+ *   - DP state is one u64 per position: cost in the high word, (match length << 16 | biased offset)
+ *     in the low word, so a relaxation is one compare and one 8-byte store; the 32 lanes relax 32
+ *     match lengths of one position per step (coalesced), strict '<' as in the reference;
+ *   - the backtrack skips literal runs 32 positions per step, records match ends newest-first, and
+ *     the emission walks that list forwards 32 sequences per step (scans for the literal / extras
+ *     cursors);
+ *   - the PivCo writer needs no trie: a symbol's path is (depth d, prefix v >> (len - d)) in the
+ *     (level, value) geometry already used by the decoder (zxc_huffman.cuh); lanes that sit on the
+ *     same node in the same step take consecutive bit slots (__match_any_sync), bits land with
+ *     atomicOr on the zeroed run area.
+ */
+#pragma once
+#include "zxc_hufenc.h"
+
+#define OPT_MATCH_COST_BASE 24u
+#define OPT_LONG_MATCH_SKIP 256u
+#define OPT_LIT_SAMPLE_MIN 1024u
+#define HUF_MIN_LITERALS 139u
+#define ENC_RAW 0u
+#define ENC_RLE 1u
+#define ENC_HUF 2u
+#define ENC_HUF_DICT 3u
+
+/* per-warp tables of one PivCo section under construction (global scratch) */
+struct PivcoPlan {
+    u32 count[HUF_MAXNODES];
+    u32 runoff[HUF_MAXNODES];
+    u32 wpos[HUF_MAXNODES];
+    u8 kind[HUF_MAXNODES];
+    u8 sorted[256];
+    unsigned short code[256]; /* canonical code value of each symbol */
+    u32 first[HUF_MAXLEN + 2], cnt[HUF_MAXLEN + 2], lbase[HUF_MAXLEN + 2], leafb[HUF_MAXLEN + 2];
+    u32 n_nodes, single, payload;
+};
+
+/* Builds the section geometry for (freq, code_len): node kinds, per-node symbol counts and run
+ * offsets.  Returns the payload size in bytes (without the 128-byte lengths header), or 0xFFFFFFFF
+ * when the lengths cannot encode this histogram (zxc_huffman.c:1042-1084, :1233-1249). */
+__device__ u32 pivco_plan(const u32* freq, const u8* code_len, PivcoPlan* T, u32 lane) {
+    u32 my_len[8];
+    u32 kraft = 0, present = 0;
+    bool bad = false;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const u32 s = 32u * (u32)r + lane;
+        const u32 l = code_len[s];
+        my_len[r] = l;
+        if (l > HUF_MAXLEN) bad = true;
+        else if (l) {
+            kraft += 1u << (HUF_MAXLEN - l);
+            present++;
+        } else if (freq[s] != 0) bad = true; /* a symbol of the histogram has no code */
+    }
+    if (__any_sync(FULL, bad)) return 0xFFFFFFFFu;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        kraft += __shfl_xor_sync(FULL, kraft, d);
+        present += __shfl_xor_sync(FULL, present, d);
+    }
+    if (present == 0) return 0xFFFFFFFFu;
+    u32 cnt[HUF_MAXLEN + 2], first[HUF_MAXLEN + 2], lbase[HUF_MAXLEN + 2], leafb[HUF_MAXLEN + 2];
+#pragma unroll
+    for (int l = 0; l <= HUF_MAXLEN + 1; l++) cnt[l] = 0;
+    u32 base_l = 0;
+    for (u32 l = 1; l <= HUF_MAXLEN; l++) {
+        u32 c_l = 0;
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const u32 m = __ballot_sync(FULL, my_len[r] == l);
+            if (my_len[r] == l) T->sorted[base_l + c_l + __popc(m & ((1u << lane) - 1u))] = (u8)(32 * r + lane);
+            c_l += __popc(m);
+        }
+        cnt[l] = c_l;
+        base_l += c_l;
+    }
+    const bool single = (present == 1 && cnt[1] == 1 && kraft == (1u << (HUF_MAXLEN - 1)));
+    if (kraft != (1u << HUF_MAXLEN) && !single) return 0xFFFFFFFFu;
+    __syncwarp();
+    if (single) {
+        const u32 c = freq[T->sorted[0]];
+        if (lane == 0) {
+            T->single = 1;
+            T->payload = (c + 7) >> 3;
+        }
+        __syncwarp();
+        return (c + 7) >> 3;
+    }
+    {
+        u32 code = 0, nodes = 1, leaves = 0;
+        first[0] = 0;
+        lbase[0] = 0;
+        leafb[0] = 0;
+        for (u32 l = 1; l <= HUF_MAXLEN; l++) {
+            code = (code + cnt[l - 1]) << 1;
+            first[l] = code;
+            lbase[l] = nodes;
+            leafb[l] = leaves;
+            nodes += (1u << l) - code;
+            leaves += cnt[l];
+        }
+        first[HUF_MAXLEN + 1] = 0;
+        lbase[HUF_MAXLEN + 1] = nodes;
+        leafb[HUF_MAXLEN + 1] = leaves;
+        if (nodes > HUF_MAXNODES) return 0xFFFFFFFFu;
+    }
+    if (lane <= HUF_MAXLEN + 1) {
+        T->first[lane] = first[lane];
+        T->cnt[lane] = cnt[lane];
+        T->lbase[lane] = lbase[lane];
+        T->leafb[lane] = leafb[lane];
+    }
+    /* canonical code of every coded symbol: first[l] + its rank among the length-l symbols */
+    for (u32 l = 1; l <= HUF_MAXLEN; l++)
+        for (u32 t = lane; t < cnt[l]; t += 32) T->code[T->sorted[leafb[l] + t]] = (unsigned short)(first[l] + t);
+    /* symbol counts, deepest level first */
+    for (int l = HUF_MAXLEN; l >= 0; l--) {
+        const u32 nn = (l == 0) ? 1u : (1u << l) - first[l];
+        for (u32 t = lane; t < nn; t += 32) {
+            const u32 id = lbase[l] + t;
+            if (l > 0 && t < cnt[l]) T->count[id] = freq[T->sorted[leafb[l] + t]];
+            else {
+                const u32 v = first[l] + t;
+                const u32 cid = lbase[l + 1] + (2u * v - first[l + 1]);
+                T->count[id] = T->count[cid] + T->count[cid + 1];
+            }
+        }
+        __syncwarp();
+    }
+    /* node kinds, parents before children (same rule as the decoder, zxc_huffman.cuh) */
+    for (u32 l = 0; l <= HUF_MAXLEN; l++) {
+        const u32 nn = (l == 0) ? 1u : (1u << l) - first[l];
+        for (u32 t = lane; t < nn; t += 32) {
+            const u32 v = first[l] + t;
+            u32 kind;
+            bool covered = false;
+            if (l > 0) {
+                const u32 pk = T->kind[lbase[l - 1] + (v >> 1) - first[l - 1]];
+                covered = (pk >= 2 && pk <= HUF_MAXLEN) || pk == HUF_KIND_COVERED;
+            }
+            const bool leaf = (l > 0) && (t < cnt[l]);
+            if (covered) kind = HUF_KIND_COVERED;
+            else if (leaf) kind = HUF_KIND_LEAF;
+            else {
+                kind = HUF_KIND_BITMAP;
+                for (u32 D = 1; l + D <= HUF_MAXLEN; D++) {
+                    const u32 lo = v << D, hi = (v + 1) << D, ld = l + D;
+                    const u32 leaf_end = first[ld] + cnt[ld];
+                    if (hi <= leaf_end) {
+                        if (D >= 2) kind = D;
+                        break;
+                    }
+                    if (lo < leaf_end) break;
+                }
+            }
+            T->kind[lbase[l] + t] = (u8)kind;
+        }
+        __syncwarp();
+    }
+    /* run offsets in BFS order */
+    const u32 total_nodes = lbase[HUF_MAXLEN + 1];
+    u32 roff = 0;
+    for (u32 i0 = 0; i0 < total_nodes; i0 += 32) {
+        const u32 id = i0 + lane;
+        u32 bytes = 0;
+        if (id < total_nodes) {
+            const u32 kind = T->kind[id], c = T->count[id];
+            if (kind == HUF_KIND_BITMAP) bytes = (c + 7) >> 3;
+            else if (kind >= 2 && kind <= HUF_MAXLEN) bytes = (c * kind + 7) >> 3;
+        }
+        const u32 inc = warp_incl_scan(bytes, lane);
+        if (id < total_nodes) {
+            T->runoff[id] = roff + inc - bytes;
+            T->wpos[id] = 0;
+        }
+        roff += __shfl_sync(FULL, inc, 31);
+    }
+    if (lane == 0) {
+        T->single = 0;
+        T->n_nodes = total_nodes;
+        T->payload = roff;
+    }
+    __syncwarp();
+    return roff;
+}
+
+/* ORs `bits` (<= 11 significant bits) into the little-endian bit stream at bit position bitpos of out */
+__device__ __forceinline__ void or_bits(u8* out, u32 bitpos, u32 bits) {
+    u8* a = out + (bitpos >> 3);
+    const uintptr_t ua = reinterpret_cast<uintptr_t>(a);
+    u32* w = reinterpret_cast<u32*>(ua & ~(uintptr_t)3);
+    const u32 sh = (u32)(ua & 3u) * 8u + (bitpos & 7u);
+    const u64 v = (u64)bits << sh;
+    if ((u32)v) atomicOr(w, (u32)v);
+    if ((u32)(v >> 32)) atomicOr(w + 1, (u32)(v >> 32));
+}
+
+/* Writes one PivCo section (optionally led by the 128-byte packed lengths) for a plan made by
+ * pivco_plan with the same (freq, code_len).  Returns bytes written. */
+__device__ u32 pivco_write(const u8* sym, u32 n, const u8* code_len, PivcoPlan* T, u8* dst, bool with_header, u32 lane) {
+    u32 hdr = 0;
+    if (with_header) {
+        for (u32 k = lane; k < 128; k += 32) dst[k] = (u8)((code_len[2 * k] & 15u) | ((code_len[2 * k + 1] & 15u) << 4));
+        hdr = 128;
+    }
+    u8* out = dst + hdr;
+    const u32 payload = T->payload;
+    for (u32 k = lane; k < payload; k += 32) out[k] = 0;
+    __syncwarp();
+    if (T->single) return hdr + payload; /* every symbol goes left at the root: all-zero bitmap */
+    u32 first[HUF_MAXLEN + 2], lbase[HUF_MAXLEN + 2];
+#pragma unroll
+    for (int l = 0; l <= HUF_MAXLEN + 1; l++) {
+        first[l] = T->first[l];
+        lbase[l] = T->lbase[l];
+    }
+    for (u32 i0 = 0; i0 < n; i0 += 32) {
+        const u32 i = i0 + lane;
+        bool active = i < n;
+        u32 l = 0, v = 0, d = 0;
+        if (active) {
+            const u32 s = sym[i];
+            l = code_len[s];
+            v = T->code[s];
+        }
+        for (;;) {
+            const u32 am = __ballot_sync(FULL, active);
+            if (!am) break;
+            if (active) {
+                const u32 id = lbase[d] + ((v >> (l - d)) - first[d]);
+                const u32 kind = T->kind[id];
+                const u32 grp = __match_any_sync(am, id);
+                const u32 rank = __popc(grp & ((1u << lane) - 1u));
+                const int leader = __ffs(grp) - 1;
+                u32 base = 0;
+                if ((int)lane == leader) {
+                    base = T->wpos[id];
+                    T->wpos[id] = base + __popc(grp);
+                }
+                base = __shfl_sync(grp, base, leader);
+                const u32 slot = base + rank;
+                if (kind == HUF_KIND_BITMAP) {
+                    const u32 bit = (v >> (l - d - 1)) & 1u;
+                    if (bit) or_bits(out + T->runoff[id], slot, 1u);
+                    d++;
+                    if (d >= l) active = false;
+                } else { /* flat root of depth `kind`: the remaining path, first branch in bit 0 */
+                    const u32 low = v & ((1u << kind) - 1u);
+                    const u32 r = __brev(low) >> (32u - kind);
+                    if (r) or_bits(out + T->runoff[id], slot * kind, r);
+                    active = false;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    __threadfence_block();
+    return hdr + payload;
+}
+
+/* byte histogram of sym[0..n) stepping by `step`, into hist[256] (shared memory, this warp's) */
+__device__ __forceinline__ u32 warp_histogram(const u8* sym, u32 n, u32 step, u32* hist, u32 lane) {
+    for (u32 k = lane; k < 256; k += 32) hist[k] = 0;
+    __syncwarp();
+    u32 cnt = 0;
+    for (u32 i = lane * step; i < n; i += 32u * step) {
+        atomicAdd(&hist[sym[i]], 1u);
+        cnt++;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(FULL, cnt, d);
+    return cnt;
+}
+
+/* extras cost of a match of length L in the DP (zxc_compress.c:904-950) */
+__device__ __forceinline__ u32 opt_match_cost(u32 L) {
+    const u32 ml = L - 5u;
+    if (ml < 15u) return OPT_MATCH_COST_BASE;
+    const u32 v = ml - 15u;
+    return OPT_MATCH_COST_BASE + (v < 128u ? 8u : (v < 16384u ? 16u : 24u));
+}
+
+struct OptOut {
+    u32 seq_c, lit_c, ext_c, max_off;
+};
+
+/* zxc_lz77_optimal_parse_glo: fills literals / tokens / offsets / extras for block bytes
+ * src[base .. base+n).  dp: n+1 u64; ends: >= n/5 + 32 u32. */
+__device__ OptOut optimal_parse(const u8* src, u32 base, u32 n, u32* head, unsigned short* chain, int level,
+                                const LzParams& lzp, u64* dp, u32* ends, u8* literals, u8* tokens,
+                                unsigned short* offsets, u8* extras, u32* hist, zxh_work_t* W, u8* cl_tmp, u32 lane) {
+    OptOut R = {0, 0, 0, 0};
+    const u8* blk = src + base;
+    if (n < 9) {
+        warp_bytes(literals, blk, n, lane);
+        R.lit_c = n;
+        return R;
+    }
+    /* literal price from a strided sample through the real code builder */
+    u32 lit_cost = 8;
+    if (n >= OPT_LIT_SAMPLE_MIN) {
+        const u32 step = n > 4096 ? (n >> 12) : 1u;
+        const u32 sampled = warp_histogram(blk, n, step, hist, lane);
+        if (lane == 0) lit_cost = zxh_estimate_lit_bits(hist, sampled, cl_tmp, W);
+        lit_cost = __shfl_sync(FULL, lit_cost, 0);
+    }
+    for (u32 k = lane; k <= n; k += 32) dp[k] = k ? 0xFFFFFFFF00000000ull : 0ull;
+    __syncwarp();
+
+    const u32 iend = base + n;
+    const u32 search_limit_pos = n - 8;
+    u32 skip_until = 0, last_off = 0;
+    for (u32 p = 0; p < n; p++) {
+        __syncwarp();
+        const u32 cur = (u32)(dp[p] >> 32);
+        if (cur == 0xFFFFFFFFu) continue;
+        const u32 lit_next = cur + lit_cost;
+        if (lane == 0 && lit_next < (u32)(dp[p + 1] >> 32)) dp[p + 1] = (u64)lit_next << 32;
+        if (p >= search_limit_pos || p < skip_until) continue;
+        const u32 ip = base + p;
+        const Match m = find_best_match(src, ip, iend, iend, ip, head, chain, level, lzp, lane, last_off);
+        if (!m.found) continue;
+        const u32 off = ip - m.ref;
+        if (off == 0 || off > ENC_WINDOW) continue;
+        last_off = off;
+        u32 L_max = m.len > n - p ? n - p : m.len;
+        if (L_max > 65535u) L_max = 65535u;
+        const u32 offb = (off - 1u) & 0xFFFFu;
+        __syncwarp(); /* lane 0's literal relaxation of dp[p+1] is not a target (L >= 5), but keep order simple */
+        for (u32 L = 5 + lane; L <= L_max; L += 32) {
+            const u32 nxt = cur + opt_match_cost(L);
+            if (nxt < (u32)(dp[p + L] >> 32)) dp[p + L] = ((u64)nxt << 32) | (L << 16) | offb;
+        }
+        if (L_max >= OPT_LONG_MATCH_SKIP) skip_until = p + L_max - 1;
+    }
+    __syncwarp();
+
+    /* backtrack: match ends, newest first */
+    u32 count = 0;
+    {
+        u32 pos = n;
+        while (pos > 0) {
+            const bool in = pos > lane;
+            const u32 q = pos - lane;
+            const u32 L = in ? (((u32)dp[q]) >> 16) : 0u;
+            const u32 hit = __ballot_sync(FULL, !in || L != 0);
+            if (!hit) {
+                pos -= 32;
+                continue;
+            }
+            const int f = __ffs(hit) - 1;
+            const u32 fin = __shfl_sync(FULL, (u32)in, f);
+            if (!fin) break; /* ran off the front through literals */
+            const u32 fq = pos - (u32)f;
+            const u32 fL = __shfl_sync(FULL, L, f);
+            if (lane == 0) ends[count] = fq;
+            count++;
+            pos = fq - fL;
+        }
+    }
+    __syncwarp();
+
+    /* forward emission, 32 sequences per step */
+    u32 lit_c = 0, ext_c = 0, max_off = 0;
+    for (u32 k0 = 0; k0 < count; k0 += 32) {
+        const u32 k = k0 + lane;
+        const bool on = k < count;
+        u32 e = 0, prev_e = 0, L = 5, offb = 0;
+        if (on) {
+            e = ends[count - 1 - k];
+            prev_e = k ? ends[count - k] : 0u;
+            const u32 lo = (u32)dp[e];
+            L = lo >> 16;
+            offb = lo & 0xFFFFu;
+        }
+        const u32 ms = e - L;
+        const u32 ll = on ? ms - prev_e : 0u;
+        const u32 ml = L - 5u;
+        u32 nb = 0;
+        if (on) {
+            if (ll >= 15u) {
+                const u32 v = ll - 15u;
+                nb += v < 128u ? 1u : (v < 16384u ? 2u : 3u);
+            }
+            if (ml >= 15u) {
+                const u32 v = ml - 15u;
+                nb += v < 128u ? 1u : (v < 16384u ? 2u : 3u);
+            }
+        }
+        const u32 s_ll = warp_incl_scan(ll, lane);
+        const u32 s_nb = warp_incl_scan(nb, lane);
+        const u32 my_lit = lit_c + s_ll - ll;
+        if (on) {
+            tokens[k] = (u8)(((ll >= 15u ? 15u : ll) << 4) | (ml >= 15u ? 15u : ml));
+            offsets[k] = (unsigned short)offb;
+            u8* x = extras + ext_c + s_nb - nb;
+            if (ll >= 15u) x += put_varint(x, ll - 15u);
+            if (ml >= 15u) put_varint(x, ml - 15u);
+        }
+        u32 mo = on ? offb : 0u;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) mo = max(mo, __shfl_xor_sync(FULL, mo, d));
+        max_off = max(max_off, mo);
+        const u32 nseq = min(32u, count - k0);
+        for (u32 j = 0; j < nseq; j++) {
+            const u32 j_ll = __shfl_sync(FULL, ll, j);
+            if (j_ll == 0) continue;
+            const u32 j_src = __shfl_sync(FULL, prev_e, j);
+            const u32 j_dst = __shfl_sync(FULL, my_lit, j);
+            warp_bytes(literals + j_dst, blk + j_src, j_ll, lane);
+        }
+        lit_c += __shfl_sync(FULL, s_ll, 31);
+        ext_c += __shfl_sync(FULL, s_nb, 31);
+    }
+    const u32 lit_start = count ? ends[0] : 0u;
+    if (lit_start < n) {
+        warp_bytes(literals + lit_c, blk + lit_start, n - lit_start, lane);
+        lit_c += n - lit_start;
+    }
+    __syncwarp();
+    R.seq_c = count;
+    R.lit_c = lit_c;
+    R.ext_c = ext_c;
+    R.max_off = max_off;
+    return R;
+}
+
+/* code lengths for one section at level >= 6: package-merge, then the nudge (lane 0; the result is
+ * in global memory for every lane after the trailing barrier).  false when no code could be built. */
+__device__ bool build_section_lengths(const u32* freq, u8* code_len, int cap, zxh_work_t* W, u32 lane) {
+    int ok = 0;
+    if (lane == 0) {
+        ok = zxh_build_code_lengths(freq, code_len, cap, W) == 0;
+        if (ok) (void)zxh_nudge_code_lengths(freq, code_len, cap, W);
+    }
+    __syncwarp();
+    return __shfl_sync(FULL, ok, 0) != 0;
+}

@@ -489,23 +489,18 @@ extern "C" int zxg_decode_pipelined(zxg_ctx* c, const uint8_t* h_src, uint64_t s
 /* frame body encode: blocks -> per-block slots -> compacted body             */
 /* ------------------------------------------------------------------------- */
 static u32 enc_staging_stride(u32 bs) { return ((bs + 8u + 68u + 4u) + 255u) & ~255u; }
-static size_t enc_scratch_stride(u32 bs) {
-    const size_t seq_cap = bs / 5 + 32;
-    size_t n = (size_t)ENC_HASH_SIZE * 4 + (size_t)ENC_WINDOW * 2 + (((size_t)bs + 63) & ~(size_t)63) + 64 +
-               seq_cap * 4 + bs / 4 + 64 + /* [dict | block] */ 65536 + bs + 64;
-    return (n + 255) & ~(size_t)255;
-}
 
 /* Encodes src into the frame BODY (all data blocks back to back) in h_body.  h_sizes receives
  * n_blocks on-disk block sizes.  Returns ZXC_OK, or ZXC_ERROR_DST_TOO_SMALL when the body does
  * not fit body_cap (then *body_size holds the size that would have been needed). */
 extern "C" int zxg_encode_body(zxg_ctx* c, const uint8_t* h_src, uint64_t src_size, uint32_t block_size, int level,
                                int checksum, uint32_t n_blocks, uint8_t* h_body, uint64_t body_cap,
-                               uint32_t* h_sizes, uint64_t* body_size, const void* h_dict, uint32_t dict_size) {
+                               uint32_t* h_sizes, uint64_t* body_size, const void* h_dict, uint32_t dict_size,
+                               const uint8_t* h_dict_huf_lens) {
     *body_size = 0;
     if (n_blocks == 0) return ZXC_OK;
     const u32 sstride = enc_staging_stride(block_size);
-    const size_t wstride = enc_scratch_stride(block_size);
+    const size_t wstride = enc_layout(block_size, level).total;
     const u32 ctas_needed = (n_blocks + ENC_WARPS_PER_CTA - 1) / ENC_WARPS_PER_CTA;
     const u32 resident = (u32)(g_sm_count > 0 ? g_sm_count : 148) * ENC_CTAS_PER_SM;
     const u32 grid = ctas_needed < resident ? ctas_needed : resident;
@@ -527,18 +522,25 @@ extern "C" int zxg_encode_body(zxg_ctx* c, const uint8_t* h_src, uint64_t src_si
     P.dict = NULL;
     P.seed_head = NULL;
     P.seed_chain = NULL;
+    P.dict_huf_lens = NULL;
     if (h_dict && dict_size) {
         /* dictionary + its seeded tables: [dict (padded)] [head 128 KB] [chain 128 KB] */
         const size_t dpad = ((size_t)dict_size + 16 + 255) & ~(size_t)255;
-        u8* d_dict = (u8*)zxg_buffer(c, ZXG_BUF_DICT, dpad + (size_t)ENC_HASH_SIZE * 4 + (size_t)ENC_WINDOW * 2);
+        const size_t dtot = dpad + (size_t)ENC_HASH_SIZE * 4 + (size_t)ENC_WINDOW * 2 + 256;
+        u8* d_dict = (u8*)zxg_buffer(c, ZXG_BUF_DICT, dtot);
         if (!d_dict) return ZXC_ERROR_MEMORY;
-        if (cudaMemsetAsync(d_dict, 0, dpad + (size_t)ENC_HASH_SIZE * 4 + (size_t)ENC_WINDOW * 2, c->stream) != cudaSuccess)
-            return ZXC_B200_ERROR_CUDA;
+        if (cudaMemsetAsync(d_dict, 0, dtot, c->stream) != cudaSuccess) return ZXC_B200_ERROR_CUDA;
         rc = zxg_h2d(c, d_dict, h_dict, dict_size);
         if (rc != ZXC_OK) return rc;
         P.dict = d_dict;
         P.seed_head = (const u32*)(d_dict + dpad);
         P.seed_chain = (const unsigned short*)(d_dict + dpad + (size_t)ENC_HASH_SIZE * 4);
+        if (h_dict_huf_lens && level >= 6) { /* the shared literal table, one length per byte */
+            u8* d_lens = d_dict + dpad + (size_t)ENC_HASH_SIZE * 4 + (size_t)ENC_WINDOW * 2;
+            rc = zxg_h2d(c, d_lens, h_dict_huf_lens, 256);
+            if (rc != ZXC_OK) return rc;
+            P.dict_huf_lens = d_lens;
+        }
         zxc_seed_kernel<<<1, 32, 0, c->stream>>>(d_dict, dict_size, (u32)level, (u32*)P.seed_head, (unsigned short*)P.seed_chain);
         __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
     }
@@ -551,7 +553,8 @@ extern "C" int zxg_encode_body(zxg_ctx* c, const uint8_t* h_src, uint64_t src_si
     P.checksum = checksum ? 1u : 0u;
     P.dict_size = P.dict ? dict_size : 0;
     if (cudaMemsetAsync(c->counter, 0, sizeof(unsigned long long), c->stream) != cudaSuccess) return ZXC_B200_ERROR_CUDA;
-    zxc_encode_kernel<<<grid, ENC_CTA_THREADS, 0, c->stream>>>(P);
+    if (level >= 6) zxc_encode_kernel<true><<<grid, ENC_CTA_THREADS, 0, c->stream>>>(P);
+    else zxc_encode_kernel<false><<<grid, ENC_CTA_THREADS, 0, c->stream>>>(P);
     __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
     if (cudaMemcpyAsync(h_sizes, d_sizes, (size_t)n_blocks * 4, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
         cudaStreamSynchronize(c->stream) != cudaSuccess) {

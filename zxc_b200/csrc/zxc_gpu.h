@@ -49,7 +49,7 @@ int zxg_decode_jobs(zxg_ctx* c, const void* d_src, void* d_dst, const zxc_b200_j
 /* Encode src into the frame body (data blocks back to back); see zxc_gpu.cu. */
 int zxg_encode_body(zxg_ctx* c, const uint8_t* h_src, uint64_t src_size, uint32_t block_size, int level,
                     int checksum, uint32_t n_blocks, uint8_t* h_body, uint64_t body_cap, uint32_t* h_sizes,
-                    uint64_t* body_size, const void* h_dict, uint32_t dict_size);
+                    uint64_t* body_size, const void* h_dict, uint32_t dict_size, const uint8_t* h_dict_huf_lens);
 
 /* 1 when the pointer is page-locked (cudaHostAlloc / cudaHostRegister / managed) */
 int zxg_host_pinned(const void* p);
