@@ -1,6 +1,6 @@
 """GPU parity for the encoder: zxc_compress through the C ABI must emit frames that are
-BYTE-IDENTICAL to the unmodified reference encoder's (levels 1-5, no dictionary), and the
-reference's golden encoder KAT (tests/format/golden.sha256) must reproduce for the covered cases."""
+BYTE-IDENTICAL to the unmodified reference encoder's (levels 1-7, with and without dictionaries),
+and the reference's golden encoder KAT (tests/format/golden.sha256) must reproduce."""
 import hashlib
 import os
 
@@ -25,6 +25,120 @@ def test_emitted_frame_identical_to_reference(prod, ref, kind, n, level):
         if a.size != b.size or not np.array_equal(a, b):
             first = int(np.argmax(a[:min(a.size, b.size)] != b[:min(a.size, b.size)])) if a.size and b.size else 0
             pytest.fail(f"{kind} L{level} bs={bs}: sizes {a.size} vs {b.size}, first diff at {first}")
+
+
+OPT_CASES = [("silesia", 1 << 20), ("text", 150000), ("random", 40000), ("numeric", 120000), ("binrec", 90000),
+             ("period1", 100000), ("period7", 100000), ("period300", 90000), ("runs", 80000), ("tiny", 1), ("small", 37),
+             ("zeros", 200000)]
+
+
+@pytest.mark.parametrize("kind,n", OPT_CASES)
+@pytest.mark.parametrize("level", [6, 7])
+def test_optimal_levels_identical_to_reference(prod, ref, kind, n, level):
+    """levels 6-7: optimal parser + Huffman literal (and, at 7, token) sections"""
+    data = make_case(kind, n)
+    for bs, cks, seek in ((65536, 0, 1), (4096, 1, 0), (0, 1, 1)):
+        if bs == 0 and n > 200000:
+            continue  # one 512 KiB block parsed by a single warp: seconds; covered by the smaller cases
+        a = ref.compress(data, level=level, block_size=bs, checksum=cks, seekable=seek)
+        b = prod.compress(data, level=level, block_size=bs, checksum=cks, seekable=seek)
+        assert not isinstance(b, int), (kind, level, bs, z.ERR.get(b, b))
+        assert a.size == b.size and np.array_equal(a, b), (kind, level, bs)
+
+
+def test_optimal_levels_use_huffman_sections(prod, ref, orc):
+    """the parity above is not vacuous: these inputs do select enc_lit = 2 / enc_tok = 2"""
+    data = make_case("text", 150000)
+    for level in (6, 7):
+        fr = prod.compress(data, level=level, block_size=65536)
+        rc, st = orc.stats(fr)
+        assert rc == 0 and st["huf_blocks"] > 0
+        r, out = prod.decompress(fr, data.size)
+        assert r == data.size and np.array_equal(out, data)
+
+
+def test_optimal_levels_with_dictionary_and_shared_table(prod, ref):
+    """dictionary-seeded optimal parse, and the dictionary's shared literal table (enc_lit = 3)"""
+    import ctypes as C
+    from test_oracle import GC_DICT, golden_dicts
+    rng = np.random.default_rng(5)
+    lines = []
+    for _ in range(400):
+        lines.append(b"GET /api/v1/users/%d/profile?session=%08x&page=%d HTTP/1.1\r\nHost: api.example.com\r\n"
+                     b"Accept: application/json\r\nUser-Agent: zxc-client\r\n\r\n"
+                     % (int(rng.integers(0, 100000)), int(rng.integers(0, 1 << 32)), int(rng.integers(0, 64))))
+    data = np.frombuffer(b"".join(lines), np.uint8)
+    # the reference's own trainer makes the shared table (the product ships no trainer)
+    ref.lib.zxc_train_dict_huf.restype = C.c_int
+    ref.lib.zxc_train_dict_huf.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+    sample = data[:4000].copy()
+    ptrs = (C.c_void_p * 1)(sample.ctypes.data)
+    sizes = (C.c_size_t * 1)(sample.size)
+    huf = np.zeros(128, np.uint8)
+    assert ref.lib.zxc_train_dict_huf(ptrs, sizes, 1, GC_DICT, len(GC_DICT), huf.ctypes.data) == 0
+    tables = [(GC_DICT, None), (GC_DICT, huf.tobytes())] + [(c, h) for c, h in golden_dicts().values()]
+    used3 = 0
+    for d, h in tables:
+        for level, bs in ((6, 4096), (7, 4096), (6, 65536), (7, 0)):
+            a = ref.compress(data, level=level, block_size=bs, seekable=1, checksum=1, dict=d, dict_huf=h)
+            b = prod.compress(data, level=level, block_size=bs, seekable=1, checksum=1, dict=d, dict_huf=h)
+            assert not isinstance(a, int), a
+            assert not isinstance(b, int), (level, bs, z.ERR.get(b, b))
+            assert a.size == b.size and np.array_equal(a, b), (level, bs, len(d), h is not None)
+            r, out = prod.decompress(b, data.size, checksum=1, dict=d, dict_huf=h)
+            assert r == data.size and np.array_equal(out, data)
+            # GLO sub-header byte 8 = enc_lit (docs/FORMAT.md 5.2) of the first data block
+            used3 += int(b[16] == 1 and b[16 + 8 + 8] == 3)
+    assert used3 > 0
+    bad = bytes([0xFF] * 128)  # lengths of 15: not a valid table -> the call fails like the reference's
+    assert prod.compress(data, level=6, dict=GC_DICT, dict_huf=bad) == ref.compress(data, level=6, dict=GC_DICT, dict_huf=bad)
+
+
+def test_golden_encoder_kat_levels_6_7(prod, ref):
+    """golden cases 05 (level 6 Huffman), 13 (level 7, 11-bit codes), 12 (shared dictionary table)"""
+    import ctypes as C
+    from test_oracle import GC_DICT
+    sha = {l.split()[1]: l.split()[0] for l in open(os.path.join(G, "format", "golden.sha256"))}
+
+    def lcg(seed):
+        s = seed
+        while True:
+            s = (s * 1103515245 + 12345) & 0xFFFFFFFF
+            yield s
+
+    alpha = b"aaaaaabbbbccdefg"
+    g = lcg(0x0BADF00D)
+    huff = np.array([alpha[(next(g) >> 16) & 15] for _ in range(16384)], np.uint8)
+    g = lcg(0x0C0FFEE1)
+    wide = np.empty(16384, np.uint8)
+    for i in range(16384):
+        u = (next(g) >> 16) & 0xFFFF
+        u2 = (u * u) >> 16
+        u4 = (u2 * u2) >> 16
+        wide[i] = (u4 * 220) >> 16
+    fr = prod.compress(huff, level=6)
+    assert hashlib.sha256(fr.tobytes()).hexdigest() == sha["05_block_glo_huffman.zxc"]
+    fr = prod.compress(wide, level=7)
+    assert hashlib.sha256(fr.tobytes()).hexdigest() == sha["13_glo_huffman_wide.zxc"]
+    # 12: payload with LCG-varied request lines, table from the reference's trainer on that payload
+    g = lcg(0x5EEDCAFE)
+    buf = b""
+    while len(buf) + 160 < 4096:
+        uid, sess, page = next(g) % 100000, next(g), next(g) % 64
+        buf += (b"GET /api/v1/users/%d/profile?session=%08x&page=%d HTTP/1.1\r\nHost: api.example.com\r\n"
+                b"Accept: application/json\r\nUser-Agent: zxc-client\r\n\r\n" % (uid, sess, page))
+    payload = np.frombuffer(buf, np.uint8).copy()
+    ref.lib.zxc_train_dict_huf.restype = C.c_int
+    ref.lib.zxc_train_dict_huf.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+    ptrs = (C.c_void_p * 1)(payload.ctypes.data)
+    sizes = (C.c_size_t * 1)(payload.size)
+    huf = np.zeros(128, np.uint8)
+    assert ref.lib.zxc_train_dict_huf(ptrs, sizes, 1, GC_DICT, len(GC_DICT), huf.ctypes.data) == 0
+    fr = prod.compress(payload, level=6, dict=GC_DICT, dict_huf=huf.tobytes())
+    assert hashlib.sha256(fr.tobytes()).hexdigest() == sha["12_glo_huffman_dict.zxc"]
+    golden = np.fromfile(os.path.join(G, "format", "12_glo_huffman_dict.zxc"), np.uint8)
+    r, out = prod.decompress(golden, payload.size, dict=GC_DICT, dict_huf=huf.tobytes())
+    assert r == payload.size and np.array_equal(out, payload)
 
 
 def test_golden_encoder_kat(prod):
@@ -118,7 +232,8 @@ def test_block_api_compress_identical(prod, ref):
     rc_ref = ref.lib.zxc_create_cctx(None)
     rc_prod = prod.lib.zxc_create_cctx(None)
     dctx = prod.lib.zxc_create_dctx()
-    for n, level, cks in ((4096, 5, 0), (65536, 3, 1), (100000, 1, 0), (700, 3, 1), (1 << 20, 4, 0), (9, 3, 0), (1, 2, 1)):
+    for n, level, cks in ((4096, 5, 0), (65536, 3, 1), (100000, 1, 0), (700, 3, 1), (1 << 20, 4, 0), (9, 3, 0), (1, 2, 1),
+                          (20000, 6, 1), (50000, 7, 0), (300, 6, 0), (8, 7, 1)):
         src = data[1000:1000 + n].copy()
         cap = int(ref.lib.zxc_compress_block_bound(n))
         a = np.zeros(cap, np.uint8)
