@@ -293,6 +293,19 @@ __device__ __forceinline__ u32 opt_match_cost(u32 L) {
     return OPT_MATCH_COST_BASE + (v < 128u ? 8u : (v < 16384u ? 16u : 24u));
 }
 
+/* common prefix of src[a..] and src[b..] (b < a) with a + len <= iend, one lane on its own; the
+ * first `known` bytes are already known equal */
+__device__ __forceinline__ u32 lane_lcp(const u8* src, u32 a, u32 b, u32 iend, u32 known) {
+    u32 len = known;
+    while (a + len + 8u <= iend) {
+        const u64 x = ldu64(src, a + len) ^ ldu64(src, b + len);
+        if (x) return len + ((u32)(__ffsll((long long)x) - 1) >> 3);
+        len += 8u;
+    }
+    while (a + len < iend && src[a + len] == src[b + len]) len++;
+    return len;
+}
+
 struct OptOut {
     u32 seq_c, lit_c, ext_c, max_off;
 };
@@ -321,30 +334,161 @@ __device__ OptOut optimal_parse(const u8* src, u32 base, u32 n, u32* head, unsig
     __syncwarp();
 
     const u32 iend = base + n;
-    const u32 search_limit_pos = n - 8;
-    u32 skip_until = 0, last_off = 0;
-    for (u32 p = 0; p < n; p++) {
+    const u32 slp = n - 8; /* positions >= slp are literal-only (ZXC_LZ_SEARCH_MARGIN) */
+    unsigned short* oldc = reinterpret_cast<unsigned short*>(hist); /* chain slots displaced by the current batch */
+    u32 p = 0, skip_until = 0, last_off = 0;
+    while (p < n) {
         __syncwarp();
-        const u32 cur = (u32)(dp[p] >> 32);
-        if (cur == 0xFFFFFFFFu) continue;
-        const u32 lit_next = cur + lit_cost;
-        if (lane == 0 && lit_next < (u32)(dp[p + 1] >> 32)) dp[p + 1] = (u64)lit_next << 32;
-        if (p >= search_limit_pos || p < skip_until) continue;
-        const u32 ip = base + p;
-        const Match m = find_best_match(src, ip, iend, iend, ip, head, chain, level, lzp, lane, last_off);
-        if (!m.found) continue;
-        const u32 off = ip - m.ref;
-        if (off == 0 || off > ENC_WINDOW) continue;
-        last_off = off;
-        u32 L_max = m.len > n - p ? n - p : m.len;
-        if (L_max > 65535u) L_max = 65535u;
-        const u32 offb = (off - 1u) & 0xFFFFu;
-        __syncwarp(); /* lane 0's literal relaxation of dp[p+1] is not a target (L >= 5), but keep order simple */
-        for (u32 L = 5 + lane; L <= L_max; L += 32) {
-            const u32 nxt = cur + opt_match_cost(L);
-            if (nxt < (u32)(dp[p + L] >> 32)) dp[p + L] = ((u64)nxt << 32) | (L << 16) | offb;
+        if (p < skip_until || p >= slp) {
+            /* literal-only stretch: dp[t] = min(dp[t], dp[t-1] + lit_cost) as a min-plus prefix scan */
+            const u32 end = p >= slp ? n : min(skip_until, slp);
+            long long carry = (long long)(u32)(dp[p] >> 32);
+            for (u32 q0 = p; q0 < end; q0 += 32) {
+                const u32 t = q0 + 1 + lane;
+                const bool on = t <= end;
+                const long long step = (long long)lit_cost * (long long)(lane + 1);
+                const long long v = on ? (long long)(u32)(dp[t] >> 32) : 0x7FFFFFFFFFFFLL;
+                long long m = v - step;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const long long o = __shfl_up_sync(FULL, m, d);
+                    if ((int)lane >= d && o < m) m = o;
+                }
+                if (carry < m) m = carry;
+                const long long fin = m + step;
+                if (on && fin < v) dp[t] = (u64)(u32)fin << 32;
+                carry = __shfl_sync(FULL, fin, 31); /* final cost at q0 + 32, the next chunk's base */
+            }
+            p = end;
+            continue;
         }
-        if (L_max >= OPT_LONG_MATCH_SKIP) skip_until = p + L_max - 1;
+        /* ---- one batch: up to 32 consecutive searched positions, one per lane ---- */
+        const u32 nact = min(32u, slp - p);
+        const u32 am = nact == 32 ? FULL : ((1u << nact) - 1u);
+        const bool act = lane < nact;
+        const u32 pos0 = base + p;
+        const u32 pos = pos0 + lane;
+        u64 cur8 = 0;
+        u32 h = 0, grp = 0, midx = 0;
+        if (act) {
+            cur8 = ldu64(src, pos);
+            h = enc_hash(cur8, true);
+            grp = __match_any_sync(am, h);
+            const u32 lower = grp & ((1u << lane) - 1u);
+            midx = lower ? pos0 + (31u - (u32)__clz(lower)) : head[h]; /* what head[h] holds once the lanes below have inserted */
+        }
+        const u32 cur_val = (u32)cur8;
+        bool skip_head = false;
+        if (act && midx) skip_head = enc_tag(ldu32(src, midx)) != enc_tag(cur_val);
+        if (act) {
+            const u32 slot = pos & (ENC_WINDOW - 1);
+            oldc[lane] = chain[slot];
+            const u32 dist = pos - midx;
+            chain[slot] = (midx != 0 && dist < ENC_WINDOW) ? (unsigned short)dist : 0;
+        }
+        __syncwarp();
+        /* lane-local chain walk (:256-437); a slot overwritten by a HIGHER lane still reads as before */
+        u32 c_len = 4, c_ref = 0;
+        bool c_found = false;
+        if (act && midx) {
+            int attempts = lzp.search_depth;
+            u32 idx = midx;
+#define OPT_RDCHAIN(q, out)                                                                   \
+    {                                                                                         \
+        const u32 jj = ((q) - pos0) & (ENC_WINDOW - 1);                                       \
+        out = (jj > lane && jj < nact) ? (u32)oldc[jj] : (u32)chain[(q) & (ENC_WINDOW - 1)];  \
+    }
+            if (skip_head) {
+                u32 delta;
+                OPT_RDCHAIN(idx, delta);
+                idx = delta ? idx - delta : 0;
+                attempts--;
+            }
+            while (idx > 0) {
+                if (attempts-- < 0 || pos - idx > ENC_MAX_DIST) break;
+                u32 delta;
+                OPT_RDCHAIN(idx, delta);
+                if (ldu32(src, idx) == cur_val) {
+                    const u32 mlen = lane_lcp(src, pos, idx, iend, 4);
+                    if (mlen > c_len) {
+                        c_len = mlen;
+                        c_ref = idx;
+                        c_found = true;
+                    }
+                    if (c_len >= (u32)lzp.sufficient_len || pos + c_len >= iend) break;
+                }
+                idx = delta ? idx - delta : 0;
+            }
+#undef OPT_RDCHAIN
+        }
+        __syncwarp();
+        /* the repeat offset a lane will most likely be probed with: the chain offset of the nearest
+         * lower lane that found a match (exact unless a repeat match won there) */
+        u32 spec;
+        {
+            const u32 fm = __ballot_sync(FULL, c_found);
+            const u32 lowerf = fm & ((1u << lane) - 1u);
+            const int sl = lowerf ? 31 - __clz(lowerf) : 0;
+            const u32 so = __shfl_sync(FULL, pos - c_ref, sl);
+            spec = lowerf ? so : last_off;
+        }
+        bool spec_eq = false;
+        if (act && spec != 0 && spec <= ENC_MAX_DIST && spec <= pos) spec_eq = ldu32(src, pos - spec) == cur_val;
+
+        /* in order: repeat-offset probe (:233-254), then the DP transitions of each position */
+        u32 valid = nact;
+        for (u32 i = 0; i < nact; i++) {
+            const u32 pi = p + i, posi = pos0 + i;
+            bool found = __shfl_sync(FULL, (u32)c_found, i) != 0;
+            u32 len = __shfl_sync(FULL, c_len, i);
+            u32 ref = __shfl_sync(FULL, c_ref, i);
+            const u32 cv = __shfl_sync(FULL, cur_val, i);
+            const u32 sp = __shfl_sync(FULL, spec, i);
+            const bool se = __shfl_sync(FULL, (u32)spec_eq, i) != 0;
+            if (last_off != 0 && last_off <= ENC_MAX_DIST && last_off <= posi) {
+                const bool eq = sp == last_off ? se : ldu32(src, posi - last_off) == cv;
+                if (eq) {
+                    const u32 rl = warp_lcp(src, posi, posi - last_off, iend, 4, 0xFFFFFFFFu, lane);
+                    const bool fin = rl >= (u32)lzp.sufficient_len || posi + rl >= iend;
+                    if (fin || !found || len <= rl) { /* ties go to the repeat offset */
+                        found = true;
+                        len = rl;
+                        ref = posi - last_off;
+                    }
+                }
+            }
+            __syncwarp();
+            const u32 cur = (u32)(dp[pi] >> 32);
+            const u32 lit_next = cur + lit_cost;
+            if (lane == 0 && lit_next < (u32)(dp[pi + 1] >> 32)) dp[pi + 1] = (u64)lit_next << 32;
+            if (!found) continue;
+            const u32 off = posi - ref;
+            last_off = off;
+            u32 L_max = len > n - pi ? n - pi : len;
+            if (L_max > 65535u) L_max = 65535u;
+            const u32 offb = (off - 1u) & 0xFFFFu;
+            for (u32 L = 5 + lane; L <= L_max; L += 32) {
+                const u32 nxt = cur + opt_match_cost(L);
+                if (nxt < (u32)(dp[pi + L] >> 32)) dp[pi + L] = ((u64)nxt << 32) | (L << 16) | offb;
+            }
+            if (L_max >= OPT_LONG_MATCH_SKIP) { /* positions inside a long match are neither searched nor inserted */
+                skip_until = pi + L_max - 1;
+                valid = i + 1;
+                break;
+            }
+        }
+        __syncwarp();
+        /* commit: head of each hash = its highest processed position; undo the inserts past `valid` */
+        if (act) {
+            const u32 vmask = valid == 32 ? FULL : ((1u << valid) - 1u);
+            const u32 grpv = grp & vmask;
+            if (lane < valid) {
+                if (lane == 31u - (u32)__clz(grpv)) head[h] = pos;
+            } else {
+                chain[pos & (ENC_WINDOW - 1)] = oldc[lane];
+            }
+        }
+        p += valid;
     }
     __syncwarp();
 
