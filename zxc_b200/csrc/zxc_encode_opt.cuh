@@ -24,6 +24,7 @@
 #pragma once
 #include "zxc_hufenc.h"
 
+#define OPT_K 4 /* positions per lane in one match-finder batch */
 #define OPT_MATCH_COST_BASE 24u
 #define OPT_LONG_MATCH_SKIP 256u
 #define OPT_LIT_SAMPLE_MIN 1024u
@@ -306,6 +307,76 @@ __device__ __forceinline__ u32 lane_lcp(const u8* src, u32 a, u32 b, u32 iend, u
     return len;
 }
 
+/* The DP front lives in registers: lane j holds the entries of positions cbase + j (A) and
+ * cbase + 32 + j (B) of the 32-aligned chunk being processed.  Transitions that land inside these 64
+ * positions are register updates; longer ones go to the global array, which is also where chunks are
+ * loaded from (already carrying those long transitions) and retired to for the backtrack. */
+struct DpFront {
+    u64 A, B;
+    u32 cbase;
+};
+#define DP_INF 0xFFFFFFFF00000000ull
+
+__device__ __forceinline__ void dp_front_init(DpFront& F, u64* dp, u32 n, u32 lane) {
+    F.cbase = 0;
+    F.A = lane <= n ? dp[lane] : DP_INF;
+    F.B = 32 + lane <= n ? dp[32 + lane] : DP_INF;
+}
+__device__ __forceinline__ void dp_front_advance(DpFront& F, u64* dp, u32 n, u32 pi, u32 lane) {
+    while (pi >= F.cbase + 32) {
+        if (F.cbase + lane <= n) dp[F.cbase + lane] = F.A;
+        F.A = F.B;
+        F.cbase += 32;
+        __syncwarp();
+        F.B = F.cbase + 32 + lane <= n ? dp[F.cbase + 32 + lane] : DP_INF;
+    }
+}
+__device__ __forceinline__ void dp_front_flush(DpFront& F, u64* dp, u32 n, u32 lane) {
+    if (F.cbase + lane <= n) dp[F.cbase + lane] = F.A;
+    if (F.cbase + 32 + lane <= n) dp[F.cbase + 32 + lane] = F.B;
+    __syncwarp();
+}
+/* all transitions out of position pi (zxc_compress.c:879-951); found/L_max/offb are warp-uniform */
+__device__ __forceinline__ void dp_front_step(DpFront& F, u64* dp, u32 n, u32 pi, u32 lit_cost, bool found, u32 L_max,
+                                              u32 offb, u32 lane) {
+    dp_front_advance(F, dp, n, pi, lane);
+    const u32 i = pi - F.cbase;
+    const u32 cur = __shfl_sync(FULL, (u32)(F.A >> 32), i);
+    if (cur == 0xFFFFFFFFu) return;
+    const u32 lit_next = cur + lit_cost;
+    if (i < 31) {
+        if (lane == i + 1 && lit_next < (u32)(F.A >> 32)) F.A = (u64)lit_next << 32;
+    } else if (lane == 0 && lit_next < (u32)(F.B >> 32)) F.B = (u64)lit_next << 32;
+    if (!found) return;
+    {
+        const u32 L = lane - i; /* target in A */
+        if (lane >= i + 5 && L <= L_max) {
+            const u32 nxt = cur + opt_match_cost(L);
+            if (nxt < (u32)(F.A >> 32)) F.A = ((u64)nxt << 32) | (L << 16) | offb;
+        }
+    }
+    {
+        const u32 L = lane + 32 - i; /* target in B */
+        if (L >= 5 && L <= L_max) {
+            const u32 nxt = cur + opt_match_cost(L);
+            if (nxt < (u32)(F.B >> 32)) F.B = ((u64)nxt << 32) | (L << 16) | offb;
+        }
+    }
+    if (L_max >= 64 - i) { /* beyond the register front */
+        for (u32 L = 64 - i + lane; L <= L_max; L += 32) {
+            const u32 nxt = cur + opt_match_cost(L);
+            if (nxt < (u32)(dp[pi + L] >> 32)) dp[pi + L] = ((u64)nxt << 32) | (L << 16) | offb;
+        }
+        __syncwarp();
+    }
+}
+
+#ifdef ZXC_OPT_PROFILE
+#define OPT_T(k) { const long long t_ = clock64(); prof[k] += t_ - tprev; tprev = t_; }
+#else
+#define OPT_T(k)
+#endif
+
 struct OptOut {
     u32 seq_c, lit_c, ext_c, max_off;
 };
@@ -336,161 +407,261 @@ __device__ OptOut optimal_parse(const u8* src, u32 base, u32 n, u32* head, unsig
     const u32 iend = base + n;
     const u32 slp = n - 8; /* positions >= slp are literal-only (ZXC_LZ_SEARCH_MARGIN) */
     unsigned short* oldc = reinterpret_cast<unsigned short*>(hist); /* chain slots displaced by the current batch */
-    u32 p = 0, skip_until = 0, last_off = 0;
+    u32 p = 0, skip_until = 0, last_off = 0, rk_pos = 0, rk_len = 0;
+#ifdef ZXC_OPT_PROFILE
+    long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+    u32 n_batches = 0, n_trunc = 0, n_arith = 0, n_spec = 0, n_load = 0, n_lcp = 0, n_far = 0;
+#endif
+    DpFront F;
+    dp_front_init(F, dp, n, lane);
     while (p < n) {
         __syncwarp();
         if (p < skip_until || p >= slp) {
-            /* literal-only stretch: dp[t] = min(dp[t], dp[t-1] + lit_cost) as a min-plus prefix scan */
+            /* literal-only stretch */
             const u32 end = p >= slp ? n : min(skip_until, slp);
-            long long carry = (long long)(u32)(dp[p] >> 32);
-            for (u32 q0 = p; q0 < end; q0 += 32) {
-                const u32 t = q0 + 1 + lane;
-                const bool on = t <= end;
-                const long long step = (long long)lit_cost * (long long)(lane + 1);
-                const long long v = on ? (long long)(u32)(dp[t] >> 32) : 0x7FFFFFFFFFFFLL;
-                long long m = v - step;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const long long o = __shfl_up_sync(FULL, m, d);
-                    if ((int)lane >= d && o < m) m = o;
-                }
-                if (carry < m) m = carry;
-                const long long fin = m + step;
-                if (on && fin < v) dp[t] = (u64)(u32)fin << 32;
-                carry = __shfl_sync(FULL, fin, 31); /* final cost at q0 + 32, the next chunk's base */
-            }
+            for (u32 q = p; q < end; q++) dp_front_step(F, dp, n, q, lit_cost, false, 0, 0, lane);
             p = end;
+            OPT_T(0)
             continue;
         }
-        /* ---- one batch: up to 32 consecutive searched positions, one per lane ---- */
-        const u32 nact = min(32u, slp - p);
-        const u32 am = nact == 32 ? FULL : ((1u << nact) - 1u);
-        const bool act = lane < nact;
+        /* ---- one batch: up to 32 * OPT_K consecutive searched positions, OPT_K per lane (position
+         * p + 32k + lane is "index" 32k + lane); the OPT_K chain walks of a lane advance in lockstep
+         * so their loads overlap ---- */
+        const u32 nact = min(32u * OPT_K, slp - p);
         const u32 pos0 = base + p;
-        const u32 pos = pos0 + lane;
-        u64 cur8 = 0;
-        u32 h = 0, grp = 0, midx = 0;
-        if (act) {
-            cur8 = ldu64(src, pos);
-            h = enc_hash(cur8, true);
-            grp = __match_any_sync(am, h);
-            const u32 lower = grp & ((1u << lane) - 1u);
-            midx = lower ? pos0 + (31u - (u32)__clz(lower)) : head[h]; /* what head[h] holds once the lanes below have inserted */
-        }
-        const u32 cur_val = (u32)cur8;
-        bool skip_head = false;
-        if (act && midx) skip_head = enc_tag(ldu32(src, midx)) != enc_tag(cur_val);
-        if (act) {
-            const u32 slot = pos & (ENC_WINDOW - 1);
-            oldc[lane] = chain[slot];
-            const u32 dist = pos - midx;
-            chain[slot] = (midx != 0 && dist < ENC_WINDOW) ? (unsigned short)dist : 0;
-        }
-        __syncwarp();
-        /* lane-local chain walk (:256-437); a slot overwritten by a HIGHER lane still reads as before */
-        u32 c_len = 4, c_ref = 0;
-        bool c_found = false;
-        if (act && midx) {
-            int attempts = lzp.search_depth;
-            u32 idx = midx;
-#define OPT_RDCHAIN(q, out)                                                                   \
-    {                                                                                         \
-        const u32 jj = ((q) - pos0) & (ENC_WINDOW - 1);                                       \
-        out = (jj > lane && jj < nact) ? (u32)oldc[jj] : (u32)chain[(q) & (ENC_WINDOW - 1)];  \
-    }
-            if (skip_head) {
-                u32 delta;
-                OPT_RDCHAIN(idx, delta);
-                idx = delta ? idx - delta : 0;
-                attempts--;
+        u32 cur_val[OPT_K], hh[OPT_K], grp[OPT_K], midx[OPT_K];
+        u64 nxt8[OPT_K]; /* bytes 4..11 after each position: the first step of every candidate compare */
+        bool skip_head[OPT_K];
+#pragma unroll
+        for (int k = 0; k < OPT_K; k++) {
+            const u32 my = 32u * k + lane;
+            const bool act = my < nact;
+            const u32 am = __ballot_sync(FULL, act);
+            const u32 pos = pos0 + my;
+            u64 cur8 = 0;
+            hh[k] = 0;
+            grp[k] = 0;
+            midx[k] = 0;
+            if (act) {
+                cur8 = ldu64(src, pos);
+                hh[k] = enc_hash(cur8, true);
+                grp[k] = __match_any_sync(am, hh[k]);
+                const u32 lower = grp[k] & ((1u << lane) - 1u);
+                /* what head[h] holds once every lower position has inserted */
+                midx[k] = lower ? pos0 + 32u * k + (31u - (u32)__clz(lower)) : head[hh[k]];
             }
-            while (idx > 0) {
-                if (attempts-- < 0 || pos - idx > ENC_MAX_DIST) break;
-                u32 delta;
-                OPT_RDCHAIN(idx, delta);
-                if (ldu32(src, idx) == cur_val) {
-                    const u32 mlen = lane_lcp(src, pos, idx, iend, 4);
-                    if (mlen > c_len) {
-                        c_len = mlen;
-                        c_ref = idx;
-                        c_found = true;
-                    }
-                    if (c_len >= (u32)lzp.sufficient_len || pos + c_len >= iend) break;
-                }
-                idx = delta ? idx - delta : 0;
-            }
-#undef OPT_RDCHAIN
-        }
-        __syncwarp();
-        /* the repeat offset a lane will most likely be probed with: the chain offset of the nearest
-         * lower lane that found a match (exact unless a repeat match won there) */
-        u32 spec;
-        {
-            const u32 fm = __ballot_sync(FULL, c_found);
-            const u32 lowerf = fm & ((1u << lane) - 1u);
-            const int sl = lowerf ? 31 - __clz(lowerf) : 0;
-            const u32 so = __shfl_sync(FULL, pos - c_ref, sl);
-            spec = lowerf ? so : last_off;
-        }
-        bool spec_eq = false;
-        if (act && spec != 0 && spec <= ENC_MAX_DIST && spec <= pos) spec_eq = ldu32(src, pos - spec) == cur_val;
-
-        /* in order: repeat-offset probe (:233-254), then the DP transitions of each position */
-        u32 valid = nact;
-        for (u32 i = 0; i < nact; i++) {
-            const u32 pi = p + i, posi = pos0 + i;
-            bool found = __shfl_sync(FULL, (u32)c_found, i) != 0;
-            u32 len = __shfl_sync(FULL, c_len, i);
-            u32 ref = __shfl_sync(FULL, c_ref, i);
-            const u32 cv = __shfl_sync(FULL, cur_val, i);
-            const u32 sp = __shfl_sync(FULL, spec, i);
-            const bool se = __shfl_sync(FULL, (u32)spec_eq, i) != 0;
-            if (last_off != 0 && last_off <= ENC_MAX_DIST && last_off <= posi) {
-                const bool eq = sp == last_off ? se : ldu32(src, posi - last_off) == cv;
-                if (eq) {
-                    const u32 rl = warp_lcp(src, posi, posi - last_off, iend, 4, 0xFFFFFFFFu, lane);
-                    const bool fin = rl >= (u32)lzp.sufficient_len || posi + rl >= iend;
-                    if (fin || !found || len <= rl) { /* ties go to the repeat offset */
-                        found = true;
-                        len = rl;
-                        ref = posi - last_off;
-                    }
-                }
+            cur_val[k] = (u32)cur8;
+            nxt8[k] = act ? ldu64(src, pos + 4) : 0;
+            skip_head[k] = act && midx[k] && enc_tag(ldu32(src, midx[k])) != enc_tag(cur_val[k]);
+            __syncwarp();
+            if (act) {
+                const u32 slot = pos & (ENC_WINDOW - 1);
+                oldc[my] = chain[slot];
+                const u32 dist = pos - midx[k];
+                chain[slot] = (midx[k] != 0 && dist < ENC_WINDOW) ? (unsigned short)dist : 0;
+                if (lane == 31u - (u32)__clz(grp[k])) head[hh[k]] = pos; /* provisional: undone on truncation */
             }
             __syncwarp();
-            const u32 cur = (u32)(dp[pi] >> 32);
-            const u32 lit_next = cur + lit_cost;
-            if (lane == 0 && lit_next < (u32)(dp[pi + 1] >> 32)) dp[pi + 1] = (u64)lit_next << 32;
-            if (!found) continue;
-            const u32 off = posi - ref;
-            last_off = off;
-            u32 L_max = len > n - pi ? n - pi : len;
-            if (L_max > 65535u) L_max = 65535u;
-            const u32 offb = (off - 1u) & 0xFFFFu;
-            for (u32 L = 5 + lane; L <= L_max; L += 32) {
-                const u32 nxt = cur + opt_match_cost(L);
-                if (nxt < (u32)(dp[pi + L] >> 32)) dp[pi + L] = ((u64)nxt << 32) | (L << 16) | offb;
+        }
+        OPT_T(1)
+        /* lane-local chain walks (:256-437); a slot overwritten by a HIGHER index still reads as before */
+        u32 c_len[OPT_K], c_ref[OPT_K], idx[OPT_K], tb[OPT_K]; /* tb: the byte a longer match must continue with */
+        int att[OPT_K];
+        bool c_found[OPT_K];
+#define OPT_RDCHAIN(q, my, out)                                                              \
+    {                                                                                        \
+        const u32 jj = ((q) - pos0) & (ENC_WINDOW - 1);                                      \
+        const u32 cv_ = chain[(q) & (ENC_WINDOW - 1)];                                       \
+        out = (jj > (my) && jj < nact) ? (u32)oldc[jj] : cv_;                                \
+    }
+#pragma unroll
+        for (int k = 0; k < OPT_K; k++) {
+            c_len[k] = 4;
+            tb[k] = (u32)nxt8[k] & 0xFFu;
+            c_ref[k] = 0;
+            c_found[k] = false;
+            att[k] = lzp.search_depth;
+            idx[k] = midx[k]; /* 0 for inactive lanes */
+            if (skip_head[k]) {
+                u32 delta;
+                OPT_RDCHAIN(idx[k], 32u * k + lane, delta);
+                idx[k] = delta ? idx[k] - delta : 0;
+                att[k]--;
             }
-            if (L_max >= OPT_LONG_MATCH_SKIP) { /* positions inside a long match are neither searched nor inserted */
-                skip_until = pi + L_max - 1;
-                valid = i + 1;
-                break;
+        }
+        for (;;) {
+            bool live = false;
+            u32 delta[OPT_K], oc[OPT_K], gb[OPT_K];
+            /* issue every load of this step before anything consumes one: the chain link and the
+             * reference's gate byte ref[best.len] (:281) -- two sectors per candidate */
+#pragma unroll
+            for (int k = 0; k < OPT_K; k++) {
+                const u32 pos = pos0 + 32u * k + lane;
+                if (idx[k] > 0 && (att[k]-- < 0 || pos - idx[k] > ENC_MAX_DIST)) idx[k] = 0;
+                const u32 q = idx[k]; /* q == 0 reads slot 0 / byte c_len: harmless, ignored below */
+                const u32 jj = (q - pos0) & (ENC_WINDOW - 1);
+                delta[k] = chain[q & (ENC_WINDOW - 1)];
+                gb[k] = src[q + c_len[k]];
+                oc[k] = oldc[jj & (32u * OPT_K - 1u)];
+            }
+#pragma unroll
+            for (int k = 0; k < OPT_K; k++) {
+                const u32 q = idx[k];
+                const u32 jj = (q - pos0) & (ENC_WINDOW - 1);
+                if (jj > 32u * k + lane && jj < nact) delta[k] = oc[k];
+            }
+#pragma unroll
+            for (int k = 0; k < OPT_K; k++) {
+                if (idx[k] == 0) continue;
+                const u32 pos = pos0 + 32u * k + lane;
+                bool stop = false;
+                /* a candidate failing the gate cannot be longer than the best so far; one passing it is
+                 * compared in full: first 4 bytes equal (:277-278), then the length */
+                if (gb[k] == tb[k] && ldu32(src, idx[k]) == cur_val[k]) {
+                    u32 mlen;
+                    const u64 x = ldu64(src, idx[k] + 4) ^ nxt8[k];
+                    if (pos + 12u > iend) mlen = lane_lcp(src, pos, idx[k], iend, 4);
+                    else if (x) mlen = 4u + ((u32)(__ffsll((long long)x) - 1) >> 3);
+                    else mlen = lane_lcp(src, pos, idx[k], iend, 12);
+                    if (mlen > c_len[k]) {
+                        c_len[k] = mlen;
+                        c_ref[k] = idx[k];
+                        c_found[k] = true;
+                        /* next gate byte: from registers while it is within bytes 4..11 (padded past iend; unused
+                         * once pos + mlen == iend, which stops the walk) */
+                        tb[k] = mlen < 12u ? (u32)(nxt8[k] >> (8u * (mlen - 4u))) & 0xFFu : (u32)src[pos + mlen];
+                    }
+                    stop = c_len[k] >= (u32)lzp.sufficient_len || pos + c_len[k] >= iend;
+                }
+                idx[k] = (stop || delta[k] == 0) ? 0 : idx[k] - delta[k];
+                live |= idx[k] > 0;
+            }
+            if (!live) break;
+        }
+#undef OPT_RDCHAIN
+        __syncwarp();
+        OPT_T(2)
+        /* the repeat offset a position will most likely be probed with: the chain offset of the nearest
+         * lower position that found a match (exact unless a repeat match won there) */
+        bool spec_eq[OPT_K];
+        u32 spec[OPT_K];
+        {
+            u32 carry = last_off;
+#pragma unroll
+            for (int k = 0; k < OPT_K; k++) {
+                const u32 pos = pos0 + 32u * k + lane;
+                const u32 fm = __ballot_sync(FULL, c_found[k]);
+                const u32 lowerf = fm & ((1u << lane) - 1u);
+                const int sl = lowerf ? 31 - __clz(lowerf) : 0;
+                const u32 so = __shfl_sync(FULL, pos - c_ref[k], sl);
+                spec[k] = lowerf ? so : carry;
+                if (fm) carry = __shfl_sync(FULL, pos - c_ref[k], 31 - __clz(fm));
+                spec_eq[k] = false;
+                if (32u * k + lane < nact && spec[k] != 0 && spec[k] <= ENC_MAX_DIST && spec[k] <= pos)
+                    spec_eq[k] = ldu32(src, pos - spec[k]) == cur_val[k];
+            }
+        }
+        OPT_T(3)
+        /* in order: repeat-offset probe (:233-254), then the DP transitions of each position */
+        u32 valid = nact;
+        bool truncated = false;
+#pragma unroll
+        for (int k = 0; k < OPT_K; k++) {
+            if (truncated || 32u * k >= nact) break;
+            const u32 gn = min(32u, nact - 32u * k);
+            for (u32 i = 0; i < gn; i++) {
+                const u32 pi = p + 32u * k + i, posi = pos0 + 32u * k + i;
+                u32 len = __shfl_sync(FULL, c_found[k] ? c_len[k] : 0u, i);
+                u32 ref = __shfl_sync(FULL, c_ref[k], i);
+                bool found = len != 0;
+                if (last_off != 0 && last_off <= ENC_MAX_DIST && last_off <= posi) {
+                    /* lcp(posi, posi - last_off): known without touching memory while posi is still inside
+                     * the last stretch measured at this offset (rk_len bytes from rk_pos) */
+                    u32 rl = 0;
+                    bool eq;
+                    if (posi - rk_pos < rk_len) {
+                        rl = rk_len - (posi - rk_pos);
+                        eq = rl >= 4;
+#ifdef ZXC_OPT_PROFILE
+                        n_arith++;
+#endif
+                    } else {
+                        const u32 sp = __shfl_sync(FULL, spec[k], i);
+#ifdef ZXC_OPT_PROFILE
+                        if (sp == last_off) n_spec++; else n_load++;
+#endif
+                        if (sp == last_off) eq = __shfl_sync(FULL, (u32)spec_eq[k], i) != 0;
+                        else eq = ldu32(src, posi - last_off) == __shfl_sync(FULL, cur_val[k], i);
+                        if (eq) rl = warp_lcp(src, posi, posi - last_off, iend, 4, 0xFFFFFFFFu, lane);
+#ifdef ZXC_OPT_PROFILE
+                        n_lcp += eq;
+#endif
+                    }
+                    if (eq) {
+                        const bool fin = rl >= (u32)lzp.sufficient_len || posi + rl >= iend;
+                        if (fin || !found || len <= rl) { /* ties go to the repeat offset */
+                            found = true;
+                            len = rl;
+                            ref = posi - last_off;
+                        }
+                    }
+                }
+                u32 L_max = 0, offb = 0;
+                if (found) {
+                    const u32 off = posi - ref;
+                    last_off = off;
+                    rk_pos = posi; /* len is the full common prefix at this offset */
+                    rk_len = len;
+                    L_max = len > n - pi ? n - pi : len;
+                    if (L_max > 65535u) L_max = 65535u;
+                    offb = (off - 1u) & 0xFFFFu;
+                }
+#ifdef ZXC_OPT_PROFILE
+                const long long t_a = clock64();
+#endif
+                dp_front_step(F, dp, n, pi, lit_cost, found, L_max, offb, lane);
+#ifdef ZXC_OPT_PROFILE
+                prof[6] += clock64() - t_a;
+                n_far += found && L_max >= 64 - ((pi) & 31u);
+#endif
+                if (L_max >= OPT_LONG_MATCH_SKIP) { /* positions inside a long match are neither searched nor inserted */
+                    skip_until = pi + L_max - 1;
+                    valid = 32u * k + i + 1;
+                    truncated = true;
+                    break;
+                }
             }
         }
         __syncwarp();
-        /* commit: head of each hash = its highest processed position; undo the inserts past `valid` */
-        if (act) {
-            const u32 vmask = valid == 32 ? FULL : ((1u << valid) - 1u);
-            const u32 grpv = grp & vmask;
-            if (lane < valid) {
-                if (lane == 31u - (u32)__clz(grpv)) head[h] = pos;
-            } else {
-                chain[pos & (ENC_WINDOW - 1)] = oldc[lane];
+        OPT_T(4)
+        if (valid != nact) {
+            /* undo the inserts past `valid`, highest first: each hash ends up pointing at what its lowest
+             * undone position had found there */
+#pragma unroll
+            for (int k = OPT_K - 1; k >= 0; k--) {
+                const u32 my = 32u * k + lane;
+                const bool inv = my >= valid && my < nact;
+                const u32 invm = __ballot_sync(FULL, inv);
+                if (inv) {
+                    chain[(pos0 + my) & (ENC_WINDOW - 1)] = oldc[my];
+                    if ((grp[k] & invm & ((1u << lane) - 1u)) == 0) head[hh[k]] = midx[k];
+                }
+                __syncwarp();
             }
         }
         p += valid;
+        OPT_T(5)
+#ifdef ZXC_OPT_PROFILE
+        n_batches++;
+        n_trunc += valid != nact;
+#endif
     }
-    __syncwarp();
+#ifdef ZXC_OPT_PROFILE
+    if (lane == 0)
+        printf("opt profile n=%u batches=%u trunc=%u | cycles: litonly %lld insert %lld walk %lld spec %lld fixup+dp %lld commit %lld | rep arith %u spec %u load %u lcp %u far %u dpstep %lld\n", n,
+               n_batches, n_trunc, prof[0], prof[1], prof[2], prof[3], prof[4], prof[5], n_arith, n_spec, n_load, n_lcp, n_far, prof[6]);
+#endif
+    dp_front_flush(F, dp, n, lane);
 
     /* backtrack: match ends, newest first */
     u32 count = 0;
