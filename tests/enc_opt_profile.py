@@ -5,7 +5,7 @@ sys.path.insert(0, __file__.rsplit("/", 1)[0])
 import zxc_ctypes as z  # noqa: E402
 from test_oracle import make_case  # noqa: E402
 prod = z.ZxcLib(z.PRODUCT_SO)
-for kind, n in (("text", 300000), ("silesia", 512 * 1024)):
+for kind, n in (("text", 65536), ("silesia", 65536), ("text", 300000), ("silesia", 512 * 1024)):
     data = make_case(kind, n)
     for level in (6, 7):
         prod.compress(data[:1000], level=level)

@@ -1,7 +1,7 @@
 """Fuzz-shaped parity corpus (replaces the reference's private fuzz corpus):
 sizes log-uniform in [0, 4 MiB], first byte selects the level as in tests/fuzz_roundtrip.c:52
 (level = data[0] % 7 + 1), content drawn from several generators.  For every input:
-  * levels 1-5: the GPU encoder's frame is byte-identical to the reference's;
+  * levels 1-7: the GPU encoder's frame is byte-identical to the reference's;
   * every level: the GPU decoder reproduces the input from the reference's frame into an
     exact-size buffer (fuzz_roundtrip.c:33-73)."""
 import numpy as np
@@ -66,3 +66,19 @@ def test_fuzz_encoder_identity(prod, ref):
         b = prod.compress(d, level=level, block_size=bs, checksum=cks, seekable=seek)
         assert not isinstance(b, int), (i, z.ERR.get(b, b))
         assert a.size == b.size and np.array_equal(a, b), (i, level, bs, d.size)
+
+
+def test_fuzz_encoder_identity_levels_6_7(prod, ref):
+    """optimal parser + Huffman sections; inputs capped at 512 KiB (a block is parsed by one warp)"""
+    rng = np.random.default_rng(4242)
+    for i in range(160):
+        d = fuzz_input(rng, 5000 + i)[: 512 << 10]
+        level = 6 + (int(d[0]) & 1 if d.size else 0)
+        bs = int(rng.choice([0, 4096, 16384, 65536, 1 << 20]))
+        cks, seek = int(rng.integers(0, 2)), int(rng.integers(0, 2))
+        a = ref.compress(d, level=level, block_size=bs, checksum=cks, seekable=seek)
+        b = prod.compress(d, level=level, block_size=bs, checksum=cks, seekable=seek)
+        assert not isinstance(b, int), (i, z.ERR.get(b, b))
+        assert a.size == b.size and np.array_equal(a, b), (i, level, bs, d.size)
+        r, out = prod.decompress(b, d.size, checksum=cks)
+        assert r == d.size and np.array_equal(out, d), (i, level, bs)

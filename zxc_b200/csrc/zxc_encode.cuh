@@ -1,7 +1,8 @@
 /*
  * zxc_encode.cuh -- sm_100a block encoder (device code only): the reference's hash-chain match
  * finder and greedy/lazy parsers for levels 1-5, one warp per independent block, emitting blocks
- * that are bit-identical to the reference encoder's.
+ * that are bit-identical to the reference encoder's.  Levels 6-7 (optimal parser, Huffman sections)
+ * share the block driver below and live in zxc_encode_opt.cuh.
  *
  * What is replicated:
  *   E1 hash            zxc_hash_func                  src/lib/zxc_compress.c:45-53
@@ -169,7 +170,7 @@ struct Match {
 
 /* zxc_lz77_find_best_match (zxc_compress.c:185-547); every lane computes the same scalars */
 __device__ Match find_best_match(const u8* src, u32 ip, u32 iend, u32 search_limit, u32 anchor, u32* head,
-                                 unsigned short* chain, int level, const LzParams& p, u32 lane, u32 last_off = 0) {
+                                 unsigned short* chain, int level, const LzParams& p, u32 lane) {
     const bool hash5 = level >= 3;
     Match best;
     best.ref = 0;
@@ -197,18 +198,7 @@ __device__ Match find_best_match(const u8* src, u32 ip, u32 iend, u32 search_lim
     __syncwarp();
 
     int attempts = p.search_depth;
-    bool rep_final = false;
-    /* repeat-offset probe (:233-254), levels 6-7 only: it wins ties against the chain candidates */
-    if (last_off != 0 && last_off <= ENC_MAX_DIST && last_off <= ip) {
-        const u32 rep = ip - last_off;
-        if (ldu32(src, rep) == cur_val) {
-            best.len = warp_lcp(src, ip, rep, iend, 4, 0xFFFFFFFFu, lane);
-            best.ref = rep;
-            best.found = true;
-            rep_final = best.len >= (u32)p.sufficient_len || ip + best.len >= iend;
-        }
-    }
-    if (match_idx != 0 && !rep_final) {
+    if (match_idx != 0) {
         if (skip_head) {
             const u32 delta = chain[match_idx & (ENC_WINDOW - 1)];
             match_idx = delta ? match_idx - delta : 0;
@@ -441,6 +431,10 @@ __device__ u32 encode_block(const EncodeParams& P, const u8* blk, u32 n, u8* dst
     u32 ip = base, anchor = base;
     u32 seq_c = 0, lit_c = 0, ext_c = 0, max_off = 0;
 
+#ifdef ZXC_OPT_PROFILE
+    const long long tb0 = clock64();
+    long long tb1 = tb0, tb2 = tb0;
+#endif
     if constexpr (OPT) {
         const OptOut R = optimal_parse(src, base, n, head, chain, level, lzp, reinterpret_cast<u64*>(scratch + lay.dp),
                                        reinterpret_cast<u32*>(scratch + lay.ends), literals, tokens, offsets, extras, hist,
@@ -511,6 +505,9 @@ __device__ u32 encode_block(const EncodeParams& P, const u8* blk, u32 n, u8* dst
     lit_c += last;
     __syncwarp();
 
+#ifdef ZXC_OPT_PROFILE
+    tb1 = clock64();
+#endif
     /* ---- section selection + serialisation.  Sizes are known before a byte is written, so a
      * block that would expand goes straight to RAW and the slot never overflows. ---- */
     u8* p = dst + 8;
@@ -577,6 +574,9 @@ __device__ u32 encode_block(const EncodeParams& P, const u8* blk, u32 n, u8* dst
             }
         }
     }
+#ifdef ZXC_OPT_PROFILE
+    tb2 = clock64();
+#endif
     const u32 off8 = max_off <= 255 ? 1u : 0u;
     const u32 sz_lit = enc_lit == ENC_RLE ? rle_sz : (enc_lit >= ENC_HUF ? huf_lit_sz : lit_c);
     const u32 sz_tok = enc_tok == ENC_HUF ? huf_tok_sz : seq_c;
@@ -654,6 +654,11 @@ __device__ u32 encode_block(const EncodeParams& P, const u8* blk, u32 n, u8* dst
         if (lane < pad) q[lane] = 0;
     }
     __syncwarp();
+#ifdef ZXC_OPT_PROFILE
+    if (OPT && lane == 0)
+        printf("block profile n=%u lit %u seq %u enc_lit %u enc_tok %u | cycles: parse %lld select %lld write %lld\n", n, lit_c, seq_c,
+               enc_lit, enc_tok, tb1 - tb0, tb2 - tb1, clock64() - tb2);
+#endif
     u32 type = ghi ? BT_GHI : BT_GLO;
     if (w >= n) {
         warp_bytes(dst + 8, blk, n, lane);

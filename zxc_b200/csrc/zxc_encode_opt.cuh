@@ -10,9 +10,20 @@
  *   code lengths          zxc_hufenc.h (package-merge + nudge; also compiled and pinned on the host)
  *
  * Mechanism (one warp per block, as for levels 1-5):
+ *   - match finding runs on batches of 32 * OPT_K consecutive positions.  The batch's inserts are
+ *     applied in position order first (same-hash positions link to each other through
+ *     __match_any_sync), then every lane walks OPT_K chains in lockstep so that the chain-link and
+ *     gate-byte loads of all walks are in flight together.  The result per position is what the
+ *     reference's sequential search returns because a walk only ever sees inserts of lower positions
+ *     (a chain slot recycled by a higher position of the batch is read from a saved copy);
+ *   - what is inherently sequential runs afterwards in position order: the repeat-offset probe (its
+ *     length is known arithmetically while inside the last stretch measured at that offset) and the
+ *     DP transitions.  A match of >= 256 bytes ends the batch there: the reference neither searches
+ *     nor inserts the positions it covers, so the later inserts are undone;
  *   - DP state is one u64 per position: cost in the high word, (match length << 16 | biased offset)
- *     in the low word, so a relaxation is one compare and one 8-byte store; the 32 lanes relax 32
- *     match lengths of one position per step (coalesced), strict '<' as in the reference;
+ *     in the low word.  The entries of the next 64 positions live in registers (two per lane); a
+ *     transition is a compare and a register move, strict '<' as in the reference, and only matches
+ *     longer than that reach the global array;
  *   - the backtrack skips literal runs 32 positions per step, records match ends newest-first, and
  *     the emission walks that list forwards 32 sequences per step (scans for the literal / extras
  *     cursors);
