@@ -764,14 +764,88 @@ __device__ OptOut optimal_parse(const u8* src, u32 base, u32 n, u32* head, unsig
     return R;
 }
 
-/* code lengths for one section at level >= 6: package-merge, then the nudge (lane 0; the result is
- * in global memory for every lane after the trailing barrier).  false when no code could be built. */
-__device__ bool build_section_lengths(const u32* freq, u8* code_len, int cap, zxh_work_t* W, u32 lane) {
+/* The nudge's grouped DP (zxh_dp_solve) with the destinations of each level spread over the lanes;
+ * zxh_dp_pull visits a destination's sources in the reference's order, so ties resolve identically. */
+__device__ int warp_dp_solve(const u64* pfg, int m, int cap_c, int lu, int g_log2, u32* out_cblc, zxh_work_t* W, u32 lane) {
+    if (m < 2 || cap_c < 1 || m > ZXH_DP_M) return 0;
+    const u32 row = (u32)(m + 1), plane = row * row;
+    u64* jcur = W->dp_a;
+    u64* jnxt = W->dp_b;
+    for (u32 i = lane; i < plane; i += 32) jcur[i] = (i == 2) ? 0ull : ZXH_U64MAX;
+    __syncwarp();
+    zxh_dp_best_t B;
+    B.j = ZXH_U64MAX;
+    B.l = B.k = B.s = 0;
+    const u32 hm = (u32)m / 2, ndest = row * hm;
+    for (int lc = 1; lc <= cap_c; lc++) {
+        u64 bj = ZXH_U64MAX;
+        u32 bk = 0;
+        for (u32 k = lane; k < (u32)m; k += 32) {
+            const u64 j = zxh_dp_finish(pfg, jcur, m, lu, g_log2, lc, k);
+            if (j < bj) {
+                bj = j;
+                bk = k;
+            }
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) { /* lowest cost, then lowest row: the first one a serial scan keeps */
+            const u64 oj = __shfl_xor_sync(FULL, bj, d);
+            const u32 ok = __shfl_xor_sync(FULL, bk, d);
+            if (oj < bj || (oj == bj && ok < bk)) {
+                bj = oj;
+                bk = ok;
+            }
+        }
+        if (bj < B.j) {
+            B.j = bj;
+            B.l = lc;
+            B.k = (int)bk;
+            B.s = m - (int)bk;
+        }
+        if (lc == cap_c) break;
+        for (u32 i = lane; i < plane; i += 32) jnxt[i] = ZXH_U64MAX;
+        __syncwarp();
+        for (u32 d = lane; d < ndest; d += 32) {
+            const u32 kd = d / hm, sd = 2u * (d % hm + 1u);
+            u32 c;
+            const u64 j = zxh_dp_pull(pfg, jcur, m, cap_c, lu, g_log2, lc, kd, sd, &c);
+            if (j != ZXH_U64MAX) {
+                jnxt[kd * row + sd] = j;
+                W->arrive[(u32)(lc + 1) * plane + kd * row + sd] = (unsigned short)c;
+            }
+        }
+        __syncwarp();
+        u64* t = jcur;
+        jcur = jnxt;
+        jnxt = t;
+    }
     int ok = 0;
+    if (lane == 0) ok = zxh_dp_backtrack(W->arrive, m, &B, out_cblc);
+    __syncwarp();
+    return __shfl_sync(FULL, ok, 0);
+}
+
+/* code lengths for one section at level >= 6: package-merge, then the nudge (serial parts on lane 0,
+ * its grouped DP warp-wide; the result is in global memory for every lane after the trailing
+ * barrier).  false when no code could be built. */
+__device__ bool build_section_lengths(const u32* freq, u8* code_len, int cap, zxh_work_t* W, u32 lane) {
+    int ok = 0, go = 0;
+    zxh_nudge_t S;
+    S.do_dp = S.m = S.cap_c = S.g_log2 = 0;
     if (lane == 0) {
         ok = zxh_build_code_lengths(freq, code_len, cap, W) == 0;
-        if (ok) (void)zxh_nudge_code_lengths(freq, code_len, cap, W);
+        if (ok) go = zxh_nudge_begin(freq, code_len, cap, W, &S);
     }
     __syncwarp();
-    return __shfl_sync(FULL, ok, 0) != 0;
+    ok = __shfl_sync(FULL, ok, 0);
+    go = __shfl_sync(FULL, go, 0);
+    if (ok && go) {
+        const int do_dp = __shfl_sync(FULL, S.do_dp, 0), m = __shfl_sync(FULL, S.m, 0);
+        const int cap_c = __shfl_sync(FULL, S.cap_c, 0), g_log2 = __shfl_sync(FULL, S.g_log2, 0);
+        int dp_ok = 0;
+        if (do_dp) dp_ok = warp_dp_solve(W->pfg, m, cap_c, ZXH_LU - g_log2, g_log2, W->cblc, W, lane);
+        if (lane == 0) (void)zxh_nudge_end(freq, code_len, W, &S, dp_ok, W->cblc);
+    }
+    __syncwarp();
+    return ok != 0;
 }

@@ -58,6 +58,7 @@ typedef struct {
     int16_t sym_order[ZXH_NSYM];
     uint8_t cand[4][ZXH_NSYM];
     uint32_t node_count[2 * ZXH_NSYM];
+    uint32_t cblc[ZXH_LU + 1]; /* grouped-DP result handed from the warp-wide solve to zxh_nudge_end */
 } zxh_work_t;
 
 ZXH unsigned zxh_log2(uint32_t v) { /* floor(log2(v)), v > 0 */
@@ -327,66 +328,59 @@ ZXH uint64_t zxh_run_cost(int lu, int lc, int g_log2, uint32_t s, uint32_t c, co
     return 256u * bits + (uint64_t)ZXH_LAMBDA_Q8 * touches;
 }
 
-/* exact DP over (groups placed, open slots) per grouped level; 1 when a solution was written */
-ZXH int zxh_dp_solve(const uint64_t* pfg, int m, int cap_c, int lu, int g_log2, uint32_t* out_cblc, zxh_work_t* W) {
-    if (m < 2 || cap_c < 1 || m > ZXH_DP_M) return 0;
+/* ---- grouped DP over (groups placed k, open slots s) per level (zxc_huffman.c:682-773) ------------
+ * The reference pushes every state's transitions forward, keeping strict improvements in (k, s, c)
+ * order.  A destination (k', s') is reached from at most one (s, c) per source row k -- c = k' - k,
+ * s = s'/2 + c -- so pulling per destination over k = 0..k' visits its candidates in the same order
+ * and keeps the same winner.  Destinations are independent: the device spreads them over the warp. */
+typedef struct {
+    uint64_t j;
+    int l, k, s;
+} zxh_dp_best_t;
+
+/* best way into state (kd, sd) at level lc + 1, coming from level lc; *out_c is the arrival choice */
+ZXH uint64_t zxh_dp_pull(const uint64_t* pfg, const uint64_t* jcur, int m, int cap_c, int lu, int g_log2, int lc, uint32_t kd,
+                         uint32_t sd, uint32_t* out_c) {
     const uint32_t row = (uint32_t)(m + 1);
-    const uint32_t plane = row * row;
-    const uint32_t arrive_cnt = (uint32_t)(cap_c + 1) * plane;
-    uint64_t* jcur = W->dp_a;
-    uint64_t* jnxt = W->dp_b;
-    uint16_t* arrive = W->arrive;
-    for (uint32_t i = 0; i < plane; i++) jcur[i] = ZXH_U64MAX;
-    jcur[0 * row + 2] = 0;
-    uint64_t best_j = ZXH_U64MAX;
-    int best_l = 0, best_k = 0, best_s = 0;
-    for (int lc = 1; lc <= cap_c; lc++) {
-        for (uint32_t i = 0; i < plane; i++) jnxt[i] = ZXH_U64MAX;
-        for (int k = 0; k < m; k++) {
-            const uint32_t n_rem = (uint32_t)(m - k);
-            for (uint32_t s = 1; s <= n_rem; s++) {
-                const uint32_t from = (uint32_t)k * row + s;
-                if (from >= plane) continue;
-                const uint64_t j0 = jcur[from];
-                if (j0 == ZXH_U64MAX) continue;
-                if (s == n_rem) { /* every remaining group fits this level: finish here */
-                    const uint64_t j = j0 + zxh_run_cost(lu, lc, g_log2, s, s, pfg, (uint32_t)k) +
-                                       (uint64_t)ZXH_LAMBDA_Q8 * (uint64_t)ZXH_LEVEL_COST * (uint64_t)(lc + g_log2 + 1);
-                    if (j < best_j) {
-                        best_j = j;
-                        best_l = lc;
-                        best_k = k;
-                        best_s = (int)s;
-                    }
-                    continue;
-                }
-                if (lc == cap_c) continue;
-                const uint64_t mm = (uint64_t)1 << (cap_c - lc);
-                const uint32_t lo = (2 * s > n_rem) ? 2 * s - n_rem : 0;
-                uint32_t hi = s - 1;
-                const uint64_t cap_hi = ((uint64_t)s * mm - n_rem) / (mm - 1);
-                if (cap_hi < hi) hi = (uint32_t)cap_hi;
-                for (uint32_t c = lo; c <= hi; c++) {
-                    const uint64_t j = j0 + zxh_run_cost(lu, lc, g_log2, s, c, pfg, (uint32_t)k);
-                    const uint32_t to = (uint32_t)(k + (int)c) * row + 2 * (s - c);
-                    const uint32_t arr = (uint32_t)(lc + 1) * plane + to;
-                    if (to >= plane || arr >= arrive_cnt) continue;
-                    if (j < jnxt[to]) {
-                        jnxt[to] = j;
-                        arrive[arr] = (uint16_t)c;
-                    }
-                }
-            }
+    const uint64_t mm = (uint64_t)1 << (cap_c - lc);
+    uint64_t best = ZXH_U64MAX;
+    uint32_t bc = 0;
+    for (uint32_t k = 0; k <= kd && k < (uint32_t)m; k++) {
+        const uint32_t c = kd - k, s = sd / 2 + c, n_rem = (uint32_t)m - k;
+        if (s >= n_rem) continue; /* s > n_rem is no state; s == n_rem must finish at lc */
+        const uint64_t j0 = jcur[k * row + s];
+        if (j0 == ZXH_U64MAX) continue;
+        const uint32_t lo = (2 * s > n_rem) ? 2 * s - n_rem : 0;
+        uint32_t hi = s - 1;
+        const uint64_t cap_hi = ((uint64_t)s * mm - n_rem) / (mm - 1);
+        if (cap_hi < hi) hi = (uint32_t)cap_hi;
+        if (c < lo || c > hi) continue;
+        const uint64_t j = j0 + zxh_run_cost(lu, lc, g_log2, s, c, pfg, k);
+        if (j < best) {
+            best = j;
+            bc = c;
         }
-        uint64_t* t = jcur;
-        jcur = jnxt;
-        jnxt = t;
     }
-    if (best_j == ZXH_U64MAX) return 0;
+    *out_c = bc;
+    return best;
+}
+
+/* cost of closing the tree at level lc from row k (state s = m - k), or U64MAX */
+ZXH uint64_t zxh_dp_finish(const uint64_t* pfg, const uint64_t* jcur, int m, int lu, int g_log2, int lc, uint32_t k) {
+    const uint32_t s = (uint32_t)m - k;
+    const uint64_t j0 = jcur[k * (uint32_t)(m + 1) + s];
+    if (j0 == ZXH_U64MAX) return ZXH_U64MAX;
+    return j0 + zxh_run_cost(lu, lc, g_log2, s, s, pfg, k) +
+           (uint64_t)ZXH_LAMBDA_Q8 * (uint64_t)ZXH_LEVEL_COST * (uint64_t)(lc + g_log2 + 1);
+}
+
+ZXH int zxh_dp_backtrack(const uint16_t* arrive, int m, const zxh_dp_best_t* B, uint32_t* out_cblc) {
+    if (B->j == ZXH_U64MAX) return 0;
+    const uint32_t row = (uint32_t)(m + 1), plane = row * row;
     for (int l = 0; l <= ZXH_LU; l++) out_cblc[l] = 0;
-    out_cblc[best_l] = (uint32_t)best_s;
-    int k = best_k, s = best_s;
-    for (int lc = best_l; lc > 1; lc--) {
+    out_cblc[B->l] = (uint32_t)B->s;
+    int k = B->k, s = B->s;
+    for (int lc = B->l; lc > 1; lc--) {
         const uint32_t c = arrive[(uint32_t)lc * plane + (uint32_t)k * row + (uint32_t)s];
         out_cblc[lc - 1] = c;
         s = s / 2 + (int)c;
@@ -395,14 +389,65 @@ ZXH int zxh_dp_solve(const uint64_t* pfg, int m, int cap_c, int lu, int g_log2, 
     return (k == 0 && s == 2) ? 1 : 0;
 }
 
-/* trades a few bytes of optimality for a flatter tree; 1 if code_len was replaced */
-ZXH int zxh_nudge_code_lengths(const uint32_t* freq, uint8_t* code_len, int max_code_len, zxh_work_t* W) {
+/* one thread's version; 1 when a solution was written */
+ZXH int zxh_dp_solve(const uint64_t* pfg, int m, int cap_c, int lu, int g_log2, uint32_t* out_cblc, zxh_work_t* W) {
+    if (m < 2 || cap_c < 1 || m > ZXH_DP_M) return 0;
+    const uint32_t row = (uint32_t)(m + 1), plane = row * row;
+    uint64_t* jcur = W->dp_a;
+    uint64_t* jnxt = W->dp_b;
+    for (uint32_t i = 0; i < plane; i++) jcur[i] = ZXH_U64MAX;
+    jcur[0 * row + 2] = 0;
+    zxh_dp_best_t B;
+    B.j = ZXH_U64MAX;
+    B.l = B.k = B.s = 0;
+    for (int lc = 1; lc <= cap_c; lc++) {
+        for (uint32_t k = 0; k < (uint32_t)m; k++) {
+            const uint64_t j = zxh_dp_finish(pfg, jcur, m, lu, g_log2, lc, k);
+            if (j < B.j) {
+                B.j = j;
+                B.l = lc;
+                B.k = (int)k;
+                B.s = m - (int)k;
+            }
+        }
+        if (lc == cap_c) break;
+        for (uint32_t i = 0; i < plane; i++) jnxt[i] = ZXH_U64MAX;
+        for (uint32_t kd = 0; kd <= (uint32_t)m; kd++) {
+            for (uint32_t sd = 2; sd <= (uint32_t)m; sd += 2) {
+                uint32_t c;
+                const uint64_t j = zxh_dp_pull(pfg, jcur, m, cap_c, lu, g_log2, lc, kd, sd, &c);
+                if (j != ZXH_U64MAX) {
+                    jnxt[kd * row + sd] = j;
+                    W->arrive[(uint32_t)(lc + 1) * plane + kd * row + sd] = (uint16_t)c;
+                }
+            }
+        }
+        uint64_t* t = jcur;
+        jcur = jnxt;
+        jnxt = t;
+    }
+    return zxh_dp_backtrack(W->arrive, m, &B, out_cblc);
+}
+
+/* The nudge in three steps so that the grouped DP in the middle can run warp-wide on the device:
+ *   zxh_nudge_begin  baseline cost, rank order, the walk and reduced-cap candidates, DP inputs
+ *   (DP)             zxh_dp_solve here; zxh_dp_pull / zxh_dp_finish spread over lanes on the device
+ *   zxh_nudge_end    DP candidate -> lengths, guard rails, adoption */
+typedef struct {
+    int n, n_cand, do_dp, m, cap_c, g_log2;
+    zxh_cost_t c0;
+} zxh_nudge_t;
+
+/* 0: alphabet too small to reshape (code_len stays); 1: continue with the DP (if S->do_dp) and _end */
+ZXH int zxh_nudge_begin(const uint32_t* freq, const uint8_t* code_len, int max_code_len, zxh_work_t* W, zxh_nudge_t* S) {
     uint32_t blc0[ZXH_LU + 1];
     const int n = zxh_classes(code_len, blc0);
+    S->n = n;
+    S->n_cand = 0;
+    S->do_dp = 0;
     if (n < 4) return 0;
     zxh_prefix_masses(code_len, freq, blc0, W->pf, W->val);
-    zxh_cost_t c0;
-    zxh_eval(blc0, W->pf, &c0);
+    zxh_eval(blc0, W->pf, &S->c0);
 
     /* symbols by descending (weight, symbol): the order lengths are handed out in */
     zxh_leaf_t* leaves = W->sort_tmp;
@@ -446,45 +491,53 @@ ZXH int zxh_nudge_code_lengths(const uint32_t* freq, uint8_t* code_len, int max_
             n_cand++;
         }
     }
-    { /* candidate 4: exact DP over groups of 1, 2 or 4 symbols */
-        const int g_log2 = n <= 64 ? 0 : (n <= 128 ? 1 : 2);
-        const int g = 1 << g_log2;
-        const int m = (n + g - 1) / g;
-        const int cap_c = max_code_len - g_log2;
-        if (m >= 2 && cap_c >= 1 && m <= (1 << cap_c)) {
-            for (int j2 = 0; j2 <= m; j2++) {
-                int r = j2 * g;
-                if (r > n) r = n;
-                W->pfg[j2] = W->pf_rank[r];
-            }
-            uint32_t cblc[ZXH_LU + 1];
-            if (zxh_dp_solve(W->pfg, m, cap_c, ZXH_LU - g_log2, g_log2, cblc, W)) {
-                uint8_t* cl = W->cand[n_cand];
-                for (int s = 0; s < ZXH_NSYM; s++) cl[s] = 0;
-                int r = 0, ghosts = 0;
-                uint8_t ghost_len = 0;
-                for (int lc = 1; lc <= cap_c; lc++) {
-                    for (uint32_t q = 0; q < cblc[lc]; q++) {
-                        for (int e = 0; e < g; e++, r++) {
-                            if (r < n) cl[W->sym_order[r]] = (uint8_t)(lc + g_log2);
-                            else {
-                                ghost_len = (uint8_t)(lc + g_log2);
-                                ghosts++;
-                            }
-                        }
+    S->n_cand = n_cand;
+    /* candidate 4: exact DP over groups of 1, 2 or 4 symbols */
+    S->g_log2 = n <= 64 ? 0 : (n <= 128 ? 1 : 2);
+    const int g = 1 << S->g_log2;
+    S->m = (n + g - 1) / g;
+    S->cap_c = max_code_len - S->g_log2;
+    if (S->m >= 2 && S->cap_c >= 1 && S->m <= (1 << S->cap_c)) {
+        for (int j2 = 0; j2 <= S->m; j2++) {
+            int r = j2 * g;
+            if (r > n) r = n;
+            W->pfg[j2] = W->pf_rank[r];
+        }
+        S->do_dp = 1;
+    }
+    return 1;
+}
+
+/* dp_ok / cblc: result of the grouped DP (ignored unless S->do_dp); 1 if code_len was replaced */
+ZXH int zxh_nudge_end(const uint32_t* freq, uint8_t* code_len, zxh_work_t* W, const zxh_nudge_t* S, int dp_ok,
+                      const uint32_t* cblc) {
+    const int n = S->n, g_log2 = S->g_log2, g = 1 << S->g_log2;
+    int n_cand = S->n_cand;
+    if (S->do_dp && dp_ok) {
+        uint8_t* cl = W->cand[n_cand];
+        for (int s = 0; s < ZXH_NSYM; s++) cl[s] = 0;
+        int r = 0, ghosts = 0;
+        uint8_t ghost_len = 0;
+        for (int lc = 1; lc <= S->cap_c; lc++) {
+            for (uint32_t q = 0; q < cblc[lc]; q++) {
+                for (int e = 0; e < g; e++, r++) {
+                    if (r < n) cl[W->sym_order[r]] = (uint8_t)(lc + g_log2);
+                    else {
+                        ghost_len = (uint8_t)(lc + g_log2);
+                        ghosts++;
                     }
                 }
-                for (int s = 0; s < ZXH_NSYM && ghosts; s++) { /* pad the last group with absent symbols */
-                    if (freq[s] == 0 && cl[s] == 0) {
-                        cl[s] = ghost_len;
-                        ghosts--;
-                    }
-                }
-                n_cand++;
             }
         }
+        for (int s = 0; s < ZXH_NSYM && ghosts; s++) { /* pad the last group with absent symbols */
+            if (freq[s] == 0 && cl[s] == 0) {
+                cl[s] = ghost_len;
+                ghosts--;
+            }
+        }
+        n_cand++;
     }
-    const uint64_t j0 = zxh_j(&c0);
+    const uint64_t j0 = zxh_j(&S->c0);
     uint64_t best_j = j0;
     int best = -1;
     for (int ci = 0; ci < n_cand; ci++) {
@@ -501,8 +554,8 @@ ZXH int zxh_nudge_code_lengths(const uint32_t* freq, uint8_t* code_len, int max_
         zxh_prefix_masses(W->cand[ci], freq, blc, W->pf, W->val);
         zxh_cost_t c1;
         zxh_eval(blc, W->pf, &c1);
-        if (c1.bits * 1000 > c0.bits * ZXH_BITS_PERMIL) continue;
-        if (c1.touches * 256 > c0.touches * ZXH_MERGE_Q8) continue;
+        if (c1.bits * 1000 > S->c0.bits * ZXH_BITS_PERMIL) continue;
+        if (c1.touches * 256 > S->c0.touches * ZXH_MERGE_Q8) continue;
         const uint64_t j = zxh_j(&c1);
         if (j < best_j) {
             best_j = j;
@@ -512,6 +565,16 @@ ZXH int zxh_nudge_code_lengths(const uint32_t* freq, uint8_t* code_len, int max_
     if (best < 0) return 0;
     for (int s = 0; s < ZXH_NSYM; s++) code_len[s] = W->cand[best][s];
     return 1;
+}
+
+/* trades a few bytes of optimality for a flatter tree; 1 if code_len was replaced */
+ZXH int zxh_nudge_code_lengths(const uint32_t* freq, uint8_t* code_len, int max_code_len, zxh_work_t* W) {
+    zxh_nudge_t S;
+    if (!zxh_nudge_begin(freq, code_len, max_code_len, W, &S)) return 0;
+    uint32_t cblc[ZXH_LU + 1];
+    int dp_ok = 0;
+    if (S.do_dp) dp_ok = zxh_dp_solve(W->pfg, S.m, S.cap_c, ZXH_LU - S.g_log2, S.g_log2, cblc, W);
+    return zxh_nudge_end(freq, code_len, W, &S, dp_ok, cblc);
 }
 
 /* ---- PivCo geometry of a canonical code (same (level, value) view as the decoder) ---------------- */
