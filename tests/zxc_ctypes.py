@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PRODUCT_SO = os.path.join(ROOT, "zxc_b200", "lib", "libzxc.so.4")
+PRODUCT_SO = os.environ.get("ZXC_B200_LIB") or os.path.join(ROOT, "zxc_b200", "lib", "libzxc.so.4")  # env: A/B builds
 ORACLE_SO = os.path.join(ROOT, "oracle", "libzxc_oracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libzxc_ref.so")
 

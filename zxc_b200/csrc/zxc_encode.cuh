@@ -675,8 +675,11 @@ __device__ u32 encode_block(const EncodeParams& P, const u8* blk, u32 n, u8* dst
     return w;
 }
 
+#ifndef ENC_OPT_MIN_CTAS
+#define ENC_OPT_MIN_CTAS 0 /* resident CTAs per SM the level 6-7 instantiation is compiled for */
+#endif
 template <bool OPT>
-__global__ void __launch_bounds__(ENC_CTA_THREADS) zxc_encode_kernel(const EncodeParams P) {
+__global__ void __launch_bounds__(ENC_CTA_THREADS, OPT ? ENC_OPT_MIN_CTAS : 0) zxc_encode_kernel(const EncodeParams P) {
     const u32 lane = threadIdx.x & 31;
     const u32 gwarp = blockIdx.x * ENC_WARPS_PER_CTA + (threadIdx.x >> 5);
     __shared__ u32 s_hist[OPT ? ENC_WARPS_PER_CTA : 1][256];

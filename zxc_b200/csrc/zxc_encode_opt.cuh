@@ -359,21 +359,24 @@ __device__ __forceinline__ void dp_front_step(DpFront& F, u64* dp, u32 n, u32 pi
         if (lane == i + 1 && lit_next < (u32)(F.A >> 32)) F.A = (u64)lit_next << 32;
     } else if (lane == 0 && lit_next < (u32)(F.B >> 32)) F.B = (u64)lit_next << 32;
     if (!found) return;
+    const u32 span_end = i + L_max;          /* last target, relative to the chunk */
+    const bool cheap = L_max < 20u;          /* every length up to L_max costs the base price (no extras byte) */
     {
         const u32 L = lane - i; /* target in A */
         if (lane >= i + 5 && L <= L_max) {
-            const u32 nxt = cur + opt_match_cost(L);
+            const u32 nxt = cur + (cheap ? OPT_MATCH_COST_BASE : opt_match_cost(L));
             if (nxt < (u32)(F.A >> 32)) F.A = ((u64)nxt << 32) | (L << 16) | offb;
         }
     }
+    if (span_end < 32) return;
     {
         const u32 L = lane + 32 - i; /* target in B */
         if (L >= 5 && L <= L_max) {
-            const u32 nxt = cur + opt_match_cost(L);
+            const u32 nxt = cur + (cheap ? OPT_MATCH_COST_BASE : opt_match_cost(L));
             if (nxt < (u32)(F.B >> 32)) F.B = ((u64)nxt << 32) | (L << 16) | offb;
         }
     }
-    if (L_max >= 64 - i) { /* beyond the register front */
+    if (span_end >= 64) { /* beyond the register front */
         for (u32 L = 64 - i + lane; L <= L_max; L += 32) {
             const u32 nxt = cur + opt_match_cost(L);
             if (nxt < (u32)(dp[pi + L] >> 32)) dp[pi + L] = ((u64)nxt << 32) | (L << 16) | offb;
