@@ -250,3 +250,35 @@ def test_block_api_compress_identical(prod, ref):
     prod.lib.zxc_free_cctx(rc_prod)
     ref.lib.zxc_free_cctx(rc_ref)
     prod.lib.zxc_free_dctx(dctx)
+
+
+def test_stream_compress_file_api(prod, ref, tmp_path):
+    """zxc_stream_compress (FILE* -> FILE*): same frame as the reference's streaming engine, dry run = size"""
+    import ctypes as C
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    data = zc.silesia_shaped(3 << 20, seed=4)[:2500000]
+    src = tmp_path / "in.bin"
+    src.write_bytes(data.tobytes())
+    for lib in (prod.lib, ref.lib):
+        lib.zxc_stream_compress.restype = C.c_int64
+        lib.zxc_stream_compress.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    for level, bs, cks, seek in ((3, 65536, 1, 1), (5, 0, 0, 0), (1, 4096, 1, 0), (6, 65536, 0, 1)):
+        o = z.CompressOpts(level=level, block_size=bs, checksum_enabled=cks, seekable=seek, n_threads=2)
+        outs = []
+        for name, lib in (("prod", prod.lib), ("ref", ref.lib)):
+            dst = tmp_path / f"{name}.zxc"
+            fi, fo = libc.fopen(str(src).encode(), b"rb"), libc.fopen(str(dst).encode(), b"wb")
+            r = lib.zxc_stream_compress(fi, fo, C.byref(o))
+            libc.fclose(fi)
+            libc.fclose(fo)
+            got = np.fromfile(dst, np.uint8)
+            assert r == got.size > 0, (name, level, r)
+            outs.append(got)
+        assert outs[0].size == outs[1].size and np.array_equal(outs[0], outs[1]), (level, bs)
+        fi = libc.fopen(str(src).encode(), b"rb")
+        assert prod.lib.zxc_stream_compress(fi, None, C.byref(o)) == outs[0].size  # dry run
+        libc.fclose(fi)
+    assert prod.lib.zxc_stream_compress(None, None, None) == -12  # ZXC_ERROR_NULL_INPUT

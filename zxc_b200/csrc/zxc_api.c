@@ -938,9 +938,29 @@ zxc_seekable* zxc_seekable_open_file(FILE* f) {
     return s;
 }
 
+/* FILE* -> FILE* compression (reference src/lib/zxc_driver.c:1035-1056).  The reference's streaming
+ * engine emits exactly the frame zxc_compress emits for the same options (checked in
+ * tests/test_encode_gpu.py), so the host side reads the input, runs the GPU frame encoder once and
+ * writes the result; f_out == NULL is the reference's dry run (size only). */
 int64_t zxc_stream_compress(FILE* f_in, FILE* f_out, const zxc_compress_opts_t* opts) {
-    (void)f_in; (void)f_out; (void)opts;
-    return ZXC_B200_ERROR_UNSUPPORTED;
+    if (!f_in) return ZXC_ERROR_NULL_INPUT;
+    const size_t block_size = (opts && opts->block_size) ? opts->block_size : ZXC_BLOCK_SIZE_DEFAULT;
+    if (!zxf_valid_block_size(block_size)) return ZXC_ERROR_BAD_BLOCK_SIZE;
+    if (opts && opts->dict && opts->dict_size > ZXC_DICT_SIZE_MAX) return ZXC_ERROR_DICT_TOO_LARGE;
+    size_t n = 0;
+    uint8_t* in = slurp(f_in, &n);
+    if (!in) return ZXC_ERROR_MEMORY;
+    if (ferror(f_in)) { free(in); return ZXC_ERROR_IO; }
+    /* blocks are block_size long, so the frame bound follows the caller's block size, not the default */
+    const uint64_t nb = (n + block_size - 1) / block_size;
+    const size_t cap = (size_t)(n + nb * (ZXF_BLOCK_HDR + ZXF_BLOCK_CKS + 64) + zxc_seek_table_size((uint32_t)(nb ? nb : 1)) + 256);
+    uint8_t* out = (uint8_t*)malloc(cap);
+    if (!out) { free(in); return ZXC_ERROR_MEMORY; }
+    int64_t r = zxc_compress(in, n, out, cap, opts);
+    if (r > 0 && f_out && fwrite(out, 1, (size_t)r, f_out) != (size_t)r) r = ZXC_ERROR_IO;
+    free(out);
+    free(in);
+    return r;
 }
 
 struct zxc_cstream_s { int unused; };
