@@ -60,14 +60,32 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md recipe).  NVML is polled
+    every 2 ms from a thread (the timed region is ~0.15 s, too short for nvidia-smi's 100 ms loop);
+    nvidia-smi is the fallback when the NVML binding is missing."""
+
+    REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         self.index = index
         self.proc = None
-        self.lines = []
+        self.lines = []  # one (sm_mhz, reasons_bitmask) per sample
+        self.max_mhz = None
+        self.stop_flag = False
+        self.nvml = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -80,33 +98,56 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.lines.append((mhz, mask))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        for l in self.lines:
-            f = [x.strip() for x in l.split(",")]
+            f = [x.strip() for x in line.split(",")]
             if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0]))
-                mx = float(f[1])
+                mhz = float(f[0])
+                self.max_mhz = float(f[1])
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+            mask = 0
+            for (name, bit), v in zip((("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+                                       ("sw_power_cap", 0x4)), f[3:7]):
                 if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                    mask |= bit
+            self.lines.append((mhz, mask))
+
+    def stop(self):
+        self.stop_flag = True
+        if self.nvml is None and not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"]}
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        else:
+            self.t.join(timeout=1)
+        sm = [m for m, _ in self.lines]
+        mask = 0
+        for _, k in self.lines:
+            mask |= k
+        reasons = sorted(name for name, bit in self.REASONS if mask & bit)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def build_shard(ref, gib, rank, seed=1):
@@ -378,188 +419,6 @@ def main():
             line["encode"] = encode_leg(6)
             line["encode"]["note"] = "configs[2]: optimal parser + Huffman sections on the GPU; levels 1-7 all encode on the GPU"
             line["encode"]["level3"] = encode_leg(LEVEL)
-        print(json.dumps(line))
-        return
-
-    # ------------------------------------------------------------------ our arm (GPU)
-    import torch
-    import torch.distributed as dist
-
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    lib = C.CDLL(z.PRODUCT_SO)  # fails loudly if the CUDA library is missing
-    prod = z.ZxcLib(z.PRODUCT_SO)
-    lib.zxc_b200_plan_frame.restype = C.c_int64
-    lib.zxc_b200_plan_frame.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
-    lib.zxc_b200_decode_scratch_size.restype = C.c_size_t
-    lib.zxc_b200_decode_scratch_size.argtypes = [C.c_uint32]
-    lib.zxc_b200_decode_blocks.restype = C.c_int
-    lib.zxc_b200_decode_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
-                                           C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_int, C.c_void_p]
-    lib.zxc_b200_reduce_status.restype = C.c_int64
-    lib.zxc_b200_reduce_status.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
-    lib.zxc_b200_launch_count.restype = C.c_uint64
-
-    data, frame, prep = build_shard(ref, args.gib, rank)
-    n = data.size
-    info = Info()
-    nb = lib.zxc_b200_plan_frame(frame.ctypes.data, frame.size, None, 0, C.byref(info))
-    assert nb > 0 and info.decoded_size == n, (nb, info.decoded_size)
-    jobs = np.zeros(nb * C.sizeof(Job), dtype=np.uint8)
-    assert lib.zxc_b200_plan_frame(frame.ctypes.data, frame.size, jobs.ctypes.data, nb, None) == nb
-    jv = jobs.view(np.dtype([("src_off", "<u8"), ("dst_off", "<u8"), ("src_len", "<u4"), ("dst_cap", "<u4")]))
-    comp_bytes = int(jv["src_len"].astype(np.int64).sum())
-    algo_bytes = comp_bytes + n  # C + U per launch
-
-    h_frame = torch.from_numpy(frame).pin_memory()
-    d_src = h_frame.to(dev, non_blocking=True)
-    d_dst = torch.empty(n, dtype=torch.uint8, device=dev)
-    d_jobs = torch.from_numpy(jobs).to(dev)
-    d_status = torch.empty(nb, dtype=torch.int32, device=dev)
-    scratch_size = lib.zxc_b200_decode_scratch_size(BLOCK)
-    d_scratch = torch.empty(scratch_size, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream(dev)
-
-    def step():
-        rc = lib.zxc_b200_decode_blocks(d_src.data_ptr(), d_dst.data_ptr(), d_jobs.data_ptr(), nb, d_status.data_ptr(),
-                                        None, 0, None, d_scratch.data_ptr(), scratch_size, BLOCK, 0, stream.cuda_stream)
-        assert rc == 0, rc
-
-    sampler = ClockSampler(local_rank)
-    sampler.start()  # nvidia-smi takes ~0.5 s to deliver its first line: start it ahead of the warm-up
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize(dev)
-    total = lib.zxc_b200_reduce_status(d_status.data_ptr(), d_jobs.data_ptr(), nb, stream.cuda_stream)
-    assert total == n, f"decode verdict {total} != {n}"
-    if not args.no_verify:
-        got = d_dst.cpu().numpy()
-        assert np.array_equal(got, data), "decoded bytes differ from the original"
-        del got
-
-    t_wait = time.time()
-    while len(sampler.lines) < 2 and time.time() - t_wait < 3.0:
-        step()  # keep the GPU under load until the sampler is live (untimed)
-        torch.cuda.synchronize(dev)
-    sampler.lines.clear()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    launches0 = lib.zxc_b200_launch_count()
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    evs[0].record(stream)
-    for i in range(args.steps):
-        step()
-        evs[i + 1].record(stream)
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    launches = int(lib.zxc_b200_launch_count() - launches0)
-    total_ms = evs[0].elapsed_time(evs[-1])
-    per_launch_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
-    clocks = sampler.stop()
-
-    t_ms = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t_ms.item()) / args.steps
-    value = (n * world) / (ms_per_step * 1e-3) / 1e9
-
-    # ---- e2e through the C ABI with host (pinned) buffers: H2D + decode + D2H every step
-    h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
-    e2e_steps = max(2, min(args.steps, 5))
-    for _ in range(2):
-        r = prod.lib.zxc_decompress(h_frame.data_ptr(), h_frame.numel(), h_out.data_ptr(), n, None)
-        assert r == n, r
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        r = prod.lib.zxc_decompress(h_frame.data_ptr(), h_frame.numel(), h_out.data_ptr(), n, None)
-    torch.cuda.synchronize(dev)
-    e2e_dt = (time.perf_counter() - t0) / e2e_steps
-    assert r == n
-    if not args.no_verify:
-        assert np.array_equal(h_out.numpy(), data), "e2e output differs"
-    t_e = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_value = (n * world) / float(t_e.item()) / 1e9
-
-    # ---- supplementary: NVLink gather of decoded output (N > 1), bounded slice
-    gather = None
-    if world > 1:
-        sl = min(n, 1 << 30)
-        outs = torch.empty(sl * world, dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(outs, d_dst[:sl])
-        torch.cuda.synchronize(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        dist.barrier()
-        e0.record()
-        for _ in range(3):
-            dist.all_gather_into_tensor(outs, d_dst[:sl])
-        e1.record()
-        torch.cuda.synchronize(dev)
-        g_ms = torch.tensor([e0.elapsed_time(e1) / 3], dtype=torch.float64, device=dev)
-        dist.all_reduce(g_ms, op=dist.ReduceOp.MAX)
-        gather = {"collective": "nccl all_gather of decoded ranges", "bytes_per_rank": sl,
-                  "gbs_per_rank_in": round(sl * (world - 1) / (float(g_ms.item()) * 1e-3) / 1e9, 1)}
-        del outs
-
-    if rank == 0:
-        peak, peak_src = measured_peak()
-        avg_launch_ms = float(np.mean(per_launch_ms))
-        achieved = algo_bytes / (avg_launch_ms * 1e-3) / 1e9
-        line = {"metric": "decompress GB/s (uncompressed)", "value": round(value, 2), "unit": "GB/s",
-                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": config,
-                "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                             "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
-                             "algorithmic_bytes_per_launch": algo_bytes, "compressed_bytes": comp_bytes,
-                             "decoded_bytes": n, "kernel": "zxc_decode_kernel", "avg_launch_ms": round(avg_launch_ms, 4),
-                             "decoded_only_frac": round((n / (avg_launch_ms * 1e-3) / 1e9) / peak, 4)},
-                "e2e": {"value": round(e2e_value, 2), "unit": "GB/s", "h2d_bytes_per_step": int(frame.size),
-                        "d2h_bytes_per_step": int(n), "api": "zxc_decompress(host frame, host dst), pinned host buffers",
-                        "steps": e2e_steps},
-                "gpu_launches": launches, "clocks": clocks, "ratio": round(frame.size / n, 4), "blocks_per_gpu": int(nb),
-                "prep": prep}
-        if gather:
-            line["gather"] = gather
-        if world == 1:
-            reps = 3
-            mt, out = cpu_reference_decode(ref, frame, n, threads, reps)
-            sample_n = min(n, 256 << 20)
-            sf = zc.compress_ref_mt(ref, data[:sample_n], level=LEVEL, block_size=BLOCK)
-            o1 = np.zeros(sample_n, dtype=np.uint8)
-            t = time.perf_counter()
-            r1 = ref.lib.zxc_decompress(sf.ctypes.data, sf.size, o1.ctypes.data, sample_n, None)
-            st = sample_n / (time.perf_counter() - t) / 1e9
-            assert r1 == sample_n
-            line["cpu_baseline"] = {"value": round(mt, 3), "unit": "GB/s", "cores": threads, "kind": "reference",
-                                    "sample": f"whole {args.gib:g} GiB frame, zxc_seekable_decompress_range_mt best of {reps}",
-                                    "single_thread_gbs": round(st, 3)}
-            # ---- supplementary: the encoder (BASELINE.json configs[2] shape at the level this build
-            # covers): 1 GiB, level 3, through zxc_compress with host buffers; frame must be byte-identical
-            enc_n = min(n, 1 << 30)
-            src_v = data[:enc_n]
-            cap = int(prod.lib.zxc_compress_bound(enc_n))
-            enc_out = np.zeros(cap, dtype=np.uint8)
-            o = z.CompressOpts(level=LEVEL, block_size=BLOCK, seekable=1)
-            r_enc = prod.lib.zxc_compress(src_v.ctypes.data, enc_n, enc_out.ctypes.data, cap, C.byref(o))  # warm-up
-            t = time.perf_counter()
-            r_enc = prod.lib.zxc_compress(src_v.ctypes.data, enc_n, enc_out.ctypes.data, cap, C.byref(o))
-            enc_dt = time.perf_counter() - t
-            t = time.perf_counter()
-            ref_frame = zc.compress_ref_mt(ref, src_v, level=LEVEL, block_size=BLOCK)
-            ref_dt = time.perf_counter() - t
-            line["encode"] = {"level": LEVEL, "bytes_in": int(enc_n), "gbs_in_e2e": round(enc_n / enc_dt / 1e9, 3),
-                              "identical_to_reference": bool(r_enc == ref_frame.size and np.array_equal(enc_out[:r_enc], ref_frame)),
-                              "cpu_reference_gbs_in": round(enc_n / ref_dt / 1e9, 3), "cpu_threads": threads,
-                              "note": "levels 1-5 are on the GPU; level 6 (configs[2]) needs the optimal parser + PivCo stage"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
