@@ -186,6 +186,17 @@ def test_argument_checks(prod):
     assert prod.lib.zxc_compress(b"abc", 3, None, 0, None) == -12
     o = z.CompressOpts(block_size=12345)
     assert prod.lib.zxc_compress(b"abc", 3, out.ctypes.data, 64, C.byref(o)) == -14
+    # FILE* entry point: argument checks come before any device work (zxc_driver.c:1035-1050)
+    prod.lib.zxc_stream_compress.restype = C.c_int64
+    prod.lib.zxc_stream_compress.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    assert prod.lib.zxc_stream_compress(None, None, None) == -12
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    f = libc.fopen(os.path.join(G, "valid", "empty.zxc").encode(), b"rb")
+    assert prod.lib.zxc_stream_compress(f, None, C.byref(o)) == -14
+    libc.fclose(f)
 
 
 @pytest.mark.skipif(has_cuda(), reason="only meaningful without a GPU")
@@ -195,3 +206,5 @@ def test_no_device_fails_loudly(prod):
     r, _ = prod.decompress(frame, 65536)
     assert r == -100 and prod.lib.zxc_error_name(r) == b"ZXC_B200_ERROR_NO_DEVICE"
     assert prod.lib.zxc_b200_device_count() == 0
+    for level in (1, 3, 6, 7):  # every level encodes on the GPU only
+        assert prod.compress(np.frombuffer(b"abcdefgh" * 64, np.uint8), level=level) == -100
