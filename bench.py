@@ -187,6 +187,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gib", type=float, default=4.0, help="decoded GiB per GPU")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--decode-only", action="store_true", help="development: skip the cpu_baseline and encode legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -382,7 +383,7 @@ def main():
                 "prep": prep}
         if gather:
             line["gather"] = gather
-        if world == 1:
+        if world == 1 and not args.decode_only:
             reps = 3
             mt, out = cpu_reference_decode(ref, frame, n, threads, reps)
             sample_n = min(n, 256 << 20)
