@@ -278,9 +278,21 @@ extern "C" int zxg_d2h(zxg_ctx* c, void* h_dst, const void* d_src, size_t bytes)
     return ZXC_OK;
 }
 
+/* resident decode CTAs per SM: CTAS_PER_SM unless ZXC_B200_DECODE_CTAS (1..CTAS_PER_SM) says fewer --
+ * a tuning knob: fewer warps keep fewer 64 KiB output windows alive in L2 */
+static u32 decode_ctas_per_sm(void) {
+    static int cached = 0;
+    if (cached == 0) {
+        const char* e = getenv("ZXC_B200_DECODE_CTAS");
+        const int v = e ? atoi(e) : 0;
+        cached = (v >= 1 && v <= (int)CTAS_PER_SM) ? v : (int)CTAS_PER_SM;
+    }
+    return (u32)cached;
+}
+
 static int grid_for(u32 n_jobs) {
     const u32 ctas_needed = (n_jobs + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    const u32 resident = (u32)(g_sm_count > 0 ? g_sm_count : 148) * CTAS_PER_SM;
+    const u32 resident = (u32)(g_sm_count > 0 ? g_sm_count : 148) * decode_ctas_per_sm();
     return (int)(ctas_needed < resident ? ctas_needed : resident);
 }
 
