@@ -35,7 +35,9 @@
 #pragma once
 #include "zxc_hufenc.h"
 
+#ifndef OPT_K
 #define OPT_K 4 /* positions per lane in one match-finder batch */
+#endif
 #define OPT_MATCH_COST_BASE 24u
 #define OPT_LONG_MATCH_SKIP 256u
 #define OPT_LIT_SAMPLE_MIN 1024u
@@ -516,7 +518,7 @@ __device__ OptOut optimal_parse(const u8* src, u32 base, u32 n, u32* head, unsig
                 const u32 jj = (q - pos0) & (ENC_WINDOW - 1);
                 delta[k] = chain[q & (ENC_WINDOW - 1)];
                 gb[k] = src[q + c_len[k]];
-                oc[k] = oldc[jj & (32u * OPT_K - 1u)];
+                oc[k] = oldc[jj < 32u * OPT_K ? jj : 0u];
             }
 #pragma unroll
             for (int k = 0; k < OPT_K; k++) {
