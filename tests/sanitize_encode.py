@@ -16,6 +16,8 @@ n = bad = 0
 cases = [("tiny", 1), ("small", 8), ("small", 9), ("small", 37), ("text", 1023), ("text", 1024), ("text", 4097), ("random", 5000),
          ("zeros", 9000), ("period7", 20000), ("runs", 30000), ("binrec", 40000), ("text", 70000), ("silesia", 140000)]
 dicts = [(None, None), (GC_DICT, None)] + [(c, h) for c, h in list(golden_dicts().values())[:1]]
+if os.environ.get("ZXC_SANITIZE_QUICK"):  # racecheck / synccheck are slow: a handful of cases
+    cases = [("small", 37), ("text", 4097), ("runs", 30000), ("silesia", 70000)]
 for kind, size in cases:
     data = make_case(kind, size)
     for level in (1, 3, 5, 6, 7):
