@@ -23,7 +23,7 @@ data = zc.silesia_shaped(1 << 20, seed=5)[:150000]
 rng = np.random.default_rng(9)
 for level, bs in ((3, 4096), (1, 4096), (6, 65536), (7, 65536)):
     frame = ref.compress(data, level=level, block_size=bs, checksum=0)
-    for t in range(60):
+    for t in range(4 if os.environ.get("ZXC_SANITIZE_QUICK") else 60):
         f = frame.copy()
         for _ in range(int(rng.integers(1, 4))):
             f[int(rng.integers(16, f.size - 12))] = int(rng.integers(0, 256))
