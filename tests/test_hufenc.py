@@ -98,3 +98,44 @@ def test_calc_size_rejects_what_the_reference_rejects(libs):
     assert h.zxhh_calc_size(f.ctypes.data, cl.ctypes.data, 1) == r.zxri_calc_size(f.ctypes.data, cl.ctypes.data, 1) == 2 ** 64 - 1
     cl[:4] = [1, 2, 3, 4]  # Kraft-incomplete
     assert h.zxhh_calc_size(f.ctypes.data, cl.ctypes.data, 1) == r.zxri_calc_size(f.ctypes.data, cl.ctypes.data, 1) == 2 ** 64 - 1
+
+
+def test_randomised_histograms_match_reference(libs):
+    """wide sweep: alphabet sizes 1..256, flat / heavy-tailed / power-of-two / tie-rich weights up to 2^21"""
+    h, r = libs
+    rng = np.random.default_rng(99)
+    adopted = 0
+    for t in range(700):
+        n_sym = int(rng.integers(1, 257))
+        f = np.zeros(256, np.uint32)
+        syms = rng.choice(256, n_sym, replace=False)
+        kind = t % 7
+        if kind == 0:
+            f[syms] = rng.integers(1, 4, n_sym)
+        elif kind == 1:
+            f[syms] = (rng.pareto(0.8, n_sym) * 100 + 1).clip(1, 2_000_000).astype(np.uint32)
+        elif kind == 2:
+            f[syms] = (2.0 ** rng.uniform(0, 21, n_sym)).astype(np.uint32)
+        elif kind == 3:
+            f[syms] = int(rng.integers(1, 1000))
+        elif kind == 4:
+            f[syms] = np.sort(rng.geometric(0.001, n_sym)).astype(np.uint32)
+        elif kind == 5:
+            f[syms] = rng.integers(1, 70000, n_sym)
+        else:
+            f[syms] = 1
+            f[syms[:max(1, n_sym // 8)]] = rng.integers(1000, 100000, max(1, n_sym // 8))
+        for cap in (8, 11):
+            base = np.zeros(256, np.uint8)
+            if r.zxri_build_code_lengths(f.ctypes.data, base.ctypes.data, cap) != 0:
+                continue
+            a = np.zeros(256, np.uint8)
+            assert h.zxhh_build_code_lengths(f.ctypes.data, a.ctypes.data, cap) == 0
+            assert np.array_equal(a, base), (t, cap)
+            b = base.copy()
+            ra = h.zxhh_nudge_code_lengths(f.ctypes.data, a.ctypes.data, cap)
+            rb = r.zxri_nudge_code_lengths(f.ctypes.data, b.ctypes.data, cap)
+            assert ra == rb and np.array_equal(a, b), (t, cap, n_sym, kind)
+            adopted += rb
+            assert h.zxhh_calc_size(f.ctypes.data, a.ctypes.data, 1) == r.zxri_calc_size(f.ctypes.data, b.ctypes.data, 1)
+    assert adopted > 100
