@@ -178,6 +178,216 @@ def cpu_reference_decode(ref, frame, n, threads, reps):
     ref.lib.zxc_seekable_free(h)
     return n / best / 1e9, out
 
+def bind_to_gpu_numa(index):
+    """Pin this process (and the pinned host buffers it allocates next) to the NUMA node of GPU `index`:
+    /sys/bus/pci/devices/<bdf>/numa_node -> that node's cpulist.  On the 8-GPU hosts GPUs 0-3 hang off node 0 and
+    4-7 off node 1; unbound ranks put every pinned buffer on one node and the 8-rank e2e collapses (round 1)."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return {"node": None, "bdf": bdf}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"node": node, "bdf": bdf, "cpus": len(allowed)}
+    except Exception as e:  # noqa: BLE001
+        return {"node": None, "error": repr(e)}
+
+
+def pipeline_leg(lib, dist, dev, stream, rank, world, frame, jv, data, steps, block):
+    """north_star's multi-GPU data path from ONE seekable frame held by rank 0 (zxc_seekable.c:999-1108):
+    partition by the SEK prefix sums (balanced compressed bytes) -> NCCL scatter of compressed block ranges ->
+    per-rank decode of the rebased job table -> NCCL gather of decoded ranges into rank 0 (which decodes its own
+    range straight into the gather buffer).  Every phase is timed on the device, max over ranks."""
+    import torch
+    from zxc_b200 import shard
+    n = data.size
+    # ---- untimed: assemble the frame on rank 0's GPU from the per-rank slices (bodies back to back)
+    body_lo = int(jv["src_off"][0])
+    body_hi = int(jv["src_off"][-1]) + int(jv["src_len"][-1])
+    sizes = torch.tensor([body_hi - body_lo, len(jv)], dtype=torch.int64, device=dev)
+    all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes)
+    body_sizes = [int(t[0]) for t in all_sizes]
+    nblocks = [int(t[1]) for t in all_sizes]
+    assert len(set(nblocks)) == 1
+    nbr = nblocks[0]
+    comp_local = torch.from_numpy(jv["src_len"].astype(np.int64)).to(dev)
+    comp_all = torch.empty(world * nbr, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(comp_all, comp_local)
+    comp_all = comp_all.cpu().numpy()
+    body_off = np.concatenate([[0], np.cumsum(body_sizes)])
+    total = n * world
+    d_body = torch.from_numpy(frame[body_lo:body_hi]).to(dev)
+    d_frame = torch.empty(16 + int(body_off[-1]), dtype=torch.uint8, device=dev) if rank == 0 else None
+    if rank == 0:
+        d_frame[:16].copy_(torch.from_numpy(frame[:16]).to(dev))
+    shard.gather_ranges_p2p(d_body, d_frame, [(16 + int(body_off[r]), 16 + int(body_off[r + 1])) for r in range(world)], dist)
+    if rank == 0:
+        d_frame[16:16 + body_sizes[0]].copy_(d_body)
+    del d_body
+    # ---- the partition every rank derives from the block table
+    parts = shard.partition_blocks(comp_all, world)
+    src_rng, dst_rng = [], []
+    for (b0, b1) in parts:
+        lo, hi, dlo, dhi = shard.rank_slice(comp_all, block, total, b0, b1)
+        src_rng.append((lo, hi))
+        dst_rng.append((dlo, dhi))
+    b0, b1 = parts[rank]
+    lo, hi = src_rng[rank]
+    dlo, dhi = dst_rng[rank]
+    nb = b1 - b0
+    jobs = np.zeros(nb, dtype=np.dtype([("src_off", "<u8"), ("dst_off", "<u8"), ("src_len", "<u4"), ("dst_cap", "<u4")]))
+    offs = 16 + np.concatenate([[0], np.cumsum(comp_all)])
+    jobs["src_off"] = offs[b0:b1] - lo
+    jobs["src_len"] = comp_all[b0:b1]
+    jobs["dst_off"] = (np.arange(b0, b1, dtype=np.int64) * block) - dlo
+    jobs["dst_cap"] = np.minimum(block, total - np.arange(b0, b1, dtype=np.int64) * block)
+    d_jobs = torch.from_numpy(jobs.view(np.uint8)).to(dev)
+    d_status = torch.empty(nb, dtype=torch.int32, device=dev)
+    ss = lib.zxc_b200_decode_scratch_size(block)
+    d_scr = torch.empty(ss, dtype=torch.uint8, device=dev)
+    d_all = torch.empty(total, dtype=torch.uint8, device=dev) if rank == 0 else None
+    d_out = d_all[dlo:dhi] if rank == 0 else torch.empty(dhi - dlo, dtype=torch.uint8, device=dev)
+
+    def run_once(ev):
+        ev[0].record(stream)
+        mine = shard.scatter_ranges_p2p(d_frame, src_rng, dist, dev)
+        ev[1].record(stream)
+        rc = lib.zxc_b200_decode_blocks(mine.data_ptr(), d_out.data_ptr(), d_jobs.data_ptr(), nb, d_status.data_ptr(),
+                                        None, 0, None, d_scr.data_ptr(), ss, block, 0, stream.cuda_stream)
+        assert rc == 0, rc
+        ev[2].record(stream)
+        shard.gather_ranges_p2p(d_out, d_all, dst_rng, dist)
+        ev[3].record(stream)
+        return mine
+    mk = lambda: [torch.cuda.Event(enable_timing=True) for _ in range(4)]  # noqa: E731
+    for _ in range(2):
+        run_once(mk())
+    torch.cuda.synchronize(dev)
+    assert lib.zxc_b200_reduce_status(d_status.data_ptr(), d_jobs.data_ptr(), nb, stream.cuda_stream) == dhi - dlo
+    # verify on rank 0: per-MiB wrapping sums of the gathered output against every rank's original slice
+    def sums(t):
+        return t.view(torch.int64).view(-1, 131072).sum(dim=1)
+    mine_sums = sums(torch.from_numpy(data).to(dev))
+    all_sums = torch.empty(world * mine_sums.numel(), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_sums, mine_sums)
+    ok = True
+    if rank == 0:
+        ok = bool(torch.equal(sums(d_all), all_sums))
+    del mine_sums, all_sums
+    dist.barrier()
+    acc = np.zeros(4)
+    for _ in range(steps):
+        ev = mk()
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        run_once(ev)
+        torch.cuda.synchronize(dev)
+        acc += [ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3]), ev[0].elapsed_time(ev[3])]
+    t = torch.tensor(acc / steps, dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sc, de, ga, tot = [float(x) for x in t.tolist()]
+    frame_bytes = int(offs[-1])
+    return {"frame": f"one seekable frame, {total / 2**30:g} GiB decoded / {frame_bytes / 2**30:.2f} GiB on disk, held by rank 0",
+            "partition": "contiguous block ranges balanced by compressed bytes (SEK prefix sums)",
+            "scatter_ms": round(sc, 3), "decode_ms": round(de, 3), "gather_ms": round(ga, 3), "total_ms": round(tot, 3),
+            "gbs_decode_only": round(total / (de * 1e-3) / 1e9, 1), "gbs_with_exchange": round(total / (tot * 1e-3) / 1e9, 1),
+            "scatter_gbs_out_of_root": round((frame_bytes - (src_rng[0][1] - src_rng[0][0])) / (sc * 1e-3) / 1e9, 1),
+            "gather_gbs_into_root": round((total - (dst_rng[0][1] - dst_rng[0][0])) / (ga * 1e-3) / 1e9, 1),
+            "nvlink_peer_copy_ref_gbs": 770.0, "collective": "NCCL grouped ncclSend/ncclRecv (batch_isend_irecv), 1 GiB messages",
+            "verified_on_rank0": ok, "steps": steps}
+
+
+def dict_leg(lib, prod, ref, dev, stream, threads, n_records, steps, peak):
+    """BASELINE.json configs[3]: 16 KiB dictionary (the reference's trainer), n x 4 KiB records, level 5, one
+    seekable frame with block_size 4096.  value = decode-only from HBM; e2e = zxc_seekable_set_dict +
+    zxc_seekable_decompress_range_mt of THIS library with host buffers; cpu = the same two calls of the reference."""
+    import torch
+    import zxc_corpus as zc
+    import zxc_ctypes as z
+    REC = 4096
+    data = zc.records(n_records, REC)
+    dict_bytes = zc.train_dict_ref(ref, data, REC)
+    dsz = len(dict_bytes)
+    frame = prod.compress(data, level=5, block_size=REC, seekable=1, dict=dict_bytes)  # GPU encoder
+    assert not isinstance(frame, int), frame
+    sub = data[: 2048 * REC]
+    identical = bool(np.array_equal(ref.compress(sub, level=5, block_size=REC, seekable=1, dict=dict_bytes),
+                                    prod.compress(sub, level=5, block_size=REC, seekable=1, dict=dict_bytes)))
+    n = data.size
+    nb = lib.zxc_b200_plan_frame(frame.ctypes.data, frame.size, None, 0, None)
+    jobs = np.zeros(nb * C.sizeof(Job), dtype=np.uint8)
+    assert lib.zxc_b200_plan_frame(frame.ctypes.data, frame.size, jobs.ctypes.data, nb, None) == nb == n_records
+    jv = jobs.view(np.dtype([("src_off", "<u8"), ("dst_off", "<u8"), ("src_len", "<u4"), ("dst_cap", "<u4")]))
+    comp_bytes = int(jv["src_len"].astype(np.int64).sum())
+    d_src = torch.from_numpy(frame).to(dev)
+    d_dst = torch.empty(n, dtype=torch.uint8, device=dev)
+    d_jobs = torch.from_numpy(jobs).to(dev)
+    d_status = torch.empty(nb, dtype=torch.int32, device=dev)
+    d_dict = torch.from_numpy(np.frombuffer(dict_bytes, np.uint8).copy()).to(dev)
+    ss = lib.zxc_b200_decode_scratch_size(REC)
+    d_scr = torch.empty(ss, dtype=torch.uint8, device=dev)
+
+    def step():
+        rc = lib.zxc_b200_decode_blocks(d_src.data_ptr(), d_dst.data_ptr(), d_jobs.data_ptr(), nb, d_status.data_ptr(),
+                                        d_dict.data_ptr(), dsz, None, d_scr.data_ptr(), ss, REC, 0, stream.cuda_stream)
+        assert rc == 0, rc
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize(dev)
+    assert lib.zxc_b200_reduce_status(d_status.data_ptr(), d_jobs.data_ptr(), nb, stream.cuda_stream) == n
+    assert np.array_equal(d_dst.cpu().numpy(), data), "dict leg: decoded records differ"
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    del d_src, d_dst, d_scr
+    # e2e through the seekable API (host buffers, pinned)
+    h_frame = torch.from_numpy(frame).pin_memory()
+    h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
+
+    def seek_run(L, fptr, flen, optr, reps):
+        h = L.zxc_seekable_open(fptr, flen)
+        assert h
+        assert L.zxc_seekable_set_dict(h, dict_bytes, dsz, None) == 0
+        best = None
+        for _ in range(reps):
+            t = time.perf_counter()
+            r = L.zxc_seekable_decompress_range_mt(h, optr, n, 0, n, threads)
+            dt = time.perf_counter() - t
+            assert r == n, r
+            best = dt if best is None or dt < best else best
+        L.zxc_seekable_free(h)
+        return n / best / 1e9
+    e2e = seek_run(prod.lib, h_frame.data_ptr(), h_frame.numel(), h_out.data_ptr(), 3)
+    assert np.array_equal(h_out.numpy(), data), "dict leg: e2e output differs"
+    out = np.zeros(n, dtype=np.uint8)
+    cpu = seek_run(ref.lib, frame.ctypes.data, frame.size, out.ctypes.data, 3)
+    assert np.array_equal(out, data)
+    achieved = (comp_bytes + n) / (ms * 1e-3) / 1e9
+    return {"workload": f"zxc_dict decode: {dsz} B dictionary (reference trainer), {n_records} x 4 KiB records, level 5, "
+                        "block_size 4096, one seekable frame",
+            "value": round(n / (ms * 1e-3) / 1e9, 2), "unit": "GB/s", "ms_per_step": round(ms, 4), "steps": steps,
+            "blocks": int(nb), "ratio": round(frame.size / n, 4), "encoder_identical_to_reference": identical,
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "algorithmic_bytes_per_launch": comp_bytes + n,
+                         "note": "C + U per record; the dictionary is read once per SM and excluded (SURVEY 8(d))"},
+            "e2e": {"value": round(e2e, 2), "unit": "GB/s", "h2d_bytes_per_step": int(frame.size), "d2h_bytes_per_step": int(n),
+                    "api": "zxc_seekable_open + zxc_seekable_set_dict + zxc_seekable_decompress_range_mt, pinned host buffers"},
+            "cpu_baseline": {"value": round(cpu, 3), "unit": "GB/s", "cores": threads, "kind": "reference",
+                             "sample": "the same frame, zxc_seekable_set_dict + zxc_seekable_decompress_range_mt, best of 3"}}
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -185,14 +395,18 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--gib", type=float, default=4.0, help="decoded GiB per GPU")
+    ap.add_argument("--gib", type=float, default=0.0, help="decoded GiB per GPU (default: 4 at one GPU = configs[1], "
+                    "8 at N > 1 so that 8 GPUs hold configs[4]'s 64 GiB frame)")
     ap.add_argument("--no-verify", action="store_true")
-    ap.add_argument("--decode-only", action="store_true", help="development: skip the cpu_baseline and encode legs")
+    ap.add_argument("--decode-only", action="store_true", help="development: skip the cpu_baseline, dict and encode legs")
+    ap.add_argument("--dict-records", type=int, default=1 << 20, help="records of the configs[3] dictionary leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gib <= 0:
+        args.gib = 4.0 if world == 1 else 8.0
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     import zxc_corpus as zc
@@ -241,6 +455,8 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -362,6 +578,11 @@ def main():
         gather = {"collective": "nccl all_gather of decoded ranges", "bytes_per_rank": sl,
                   "gbs_per_rank_in": round(sl * (world - 1) / (float(g_ms.item()) * 1e-3) / 1e9, 1)}
         del outs
+    pipeline = None
+    if world > 1:
+        del d_scratch
+        torch.cuda.empty_cache()
+        pipeline = pipeline_leg(lib, dist, dev, stream, rank, world, frame, jv, data, max(2, min(args.steps, 5)), BLOCK)
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -383,7 +604,12 @@ def main():
                 "prep": prep}
         if gather:
             line["gather"] = gather
+        if pipeline:
+            line["pipeline"] = pipeline
+        line["numa"] = numa
         if world == 1 and not args.decode_only:
+            os.sched_setaffinity(0, all_cpus)  # the CPU baseline may use every host core again
+            threads = zc.host_threads()
             reps = 3
             mt, out = cpu_reference_decode(ref, frame, n, threads, reps)
             sample_n = min(n, 256 << 20)
@@ -417,6 +643,9 @@ def main():
                         "ratio": round(r_enc / enc_n, 4),
                         "cpu_reference_gbs_in": round(enc_n / ref_dt / 1e9, 3), "cpu_threads": threads}
 
+            del d_src, d_dst
+            torch.cuda.empty_cache()
+            line["dict"] = dict_leg(lib, prod, ref, dev, stream, threads, args.dict_records, max(3, args.steps), peak)
             line["encode"] = encode_leg(6)
             line["encode"]["note"] = "configs[2]: optimal parser + Huffman sections on the GPU; levels 1-7 all encode on the GPU"
             line["encode"]["level3"] = encode_leg(LEVEL)

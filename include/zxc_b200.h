@@ -27,7 +27,8 @@
 extern "C" {
 #endif
 
-/* One independent block = one warp's unit of work.  Replaces the reference's
+/* One independent block = one unit of work (a CTA of the block-cooperative kernel, or a warp of
+ * the general kernel).  Replaces the reference's
  * zxc_seek_mt_job_t (src/lib/zxc_seekable.c:802-815). */
 typedef struct {
     uint64_t src_off; /* byte offset of the 8-byte block header inside the source buffer */
@@ -52,9 +53,9 @@ ZXC_EXPORT int zxc_b200_device_count(void);
 
 /* Walk a frame held in HOST memory and fill jobs[0..n) (dst offsets assume every
  * block but the last decodes to block_size, which the decode then verifies).
- * Uses the SEK table when present, else the sequential header walk of
- * zxc_decompress_frame (src/lib/zxc_dispatch.c:912-1001).  jobs may be NULL to
- * query the count.  Returns the number of blocks or a negative zxc_error_t. */
+ * Always the sequential header walk of zxc_decompress_frame (src/lib/zxc_dispatch.c:912-1001),
+ * so damaged block headers are reported exactly as the reference reports them; the SEK
+ * table is only probed to fill info->seekable.  jobs may be NULL to query the count.  Returns the number of blocks or a negative zxc_error_t. */
 ZXC_EXPORT int64_t zxc_b200_plan_frame(const void* frame, size_t frame_size, zxc_b200_job_t* jobs,
                                        size_t max_jobs, zxc_b200_frame_info_t* info);
 

@@ -98,3 +98,50 @@ def test_scatter_decode_gather_world2(tmp_path):
     res.sort()
     assert all(r[1] is True for r in res), res
     assert res[0][2] == 0 and res[0][3] == res[1][2] and res[1][3] == 48
+
+
+def _p2p_worker(rank, world, port, q):
+    try:
+        import torch
+        import torch.distributed as dist
+        from zxc_b200 import shard
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        shard.CHUNK = 1000  # several messages per range
+        rng = np.random.default_rng(1)
+        frame = torch.from_numpy(rng.integers(0, 256, 10000, dtype=np.uint8)) if rank == 0 else None
+        ranges = [(16, 4211), (4211, 10000)]
+        mine = shard.scatter_ranges_p2p(frame, ranges, dist, "cpu")
+        ref = np.random.default_rng(1).integers(0, 256, 10000, dtype=np.uint8)
+        lo, hi = ranges[rank]
+        ok = np.array_equal(mine.numpy(), ref[lo:hi])
+        # the inverse: every rank contributes its (transformed) range, rank 0 ends up with all of it
+        out_rng = [(0, 3000), (3000, 7777)]
+        dec = torch.full((out_rng[rank][1] - out_rng[rank][0],), rank + 1, dtype=torch.uint8)
+        whole = torch.zeros(7777, dtype=torch.uint8) if rank == 0 else None
+        if rank == 0:
+            whole[0:3000].copy_(dec)  # the root decodes in place
+        shard.gather_ranges_p2p(dec, whole, out_rng, dist)
+        if rank == 0:
+            ok = ok and bool((whole[:3000] == 1).all()) and bool((whole[3000:] == 2).all())
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, bool(ok)))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+
+
+def test_p2p_scatter_gather_world2():
+    """the batched send/recv exchange bench.py's pipeline leg runs over NCCL, here over gloo"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_p2p_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)], res

@@ -60,6 +60,38 @@ def silesia_shaped(n, seed=1, out=None, threads=None, offset=0):
     return out
 
 
+def records(n, record_size=4096, seed=7):
+    """n fixed-size JSON-ish records (BASELINE.json configs[3]), generated in parallel."""
+    lib = _corpus()
+    lib.zxcorp_records.restype = C.c_int
+    lib.zxcorp_records.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64]
+    out = np.empty(n * record_size, np.uint8)
+    th = host_threads()
+    per = (n + th - 1) // th
+
+    def work(i):
+        lo = i * per
+        if lo < n:
+            lib.zxcorp_records(out.ctypes.data + lo * record_size, lo, min(per, n - lo), record_size, seed)
+
+    with ThreadPoolExecutor(th) as ex:
+        list(ex.map(work, range(th)))
+    return out
+
+
+def train_dict_ref(ref, data, record_size=4096, n_samples=4096, cap=16384):
+    """dictionary bytes from the reference's own trainer (zxc_train_dict) over the first n_samples records"""
+    ref.lib.zxc_train_dict.restype = C.c_int64
+    ref.lib.zxc_train_dict.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    ns = min(n_samples, data.size // record_size)
+    ptrs = (C.c_void_p * ns)(*[data.ctypes.data + i * record_size for i in range(ns)])
+    sizes = (C.c_size_t * ns)(*([record_size] * ns))
+    dbuf = np.zeros(cap, np.uint8)
+    dsz = ref.lib.zxc_train_dict(ptrs, sizes, ns, dbuf.ctypes.data, dbuf.size)
+    assert dsz > 0, dsz
+    return dbuf[:dsz].tobytes()
+
+
 # ---- small generators (reference tests/test_common.c:35-135 equivalents) -------
 def gen_random(n, seed=42):
     return np.random.default_rng(seed).integers(0, 256, n, dtype=np.uint8)

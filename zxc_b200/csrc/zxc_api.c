@@ -360,6 +360,7 @@ static int64_t decompress_frame(zxg_ctx* g, const uint8_t* src, size_t src_size,
     const size_t dict_size = (opts && opts->dict) ? opts->dict_size : 0;
     const uint8_t* dict_huf = (opts && opts->dict) ? (const uint8_t*)opts->dict_huf : NULL;
 
+    if (dict_size > ZXC_DICT_SIZE_MAX) return ZXC_ERROR_DICT_TOO_LARGE; /* zxc_dispatch.c:671 */
     zxw_walk_t w;
     const int wrc = zxw_walk(src, src_size, &w);
     if (wrc != ZXC_OK) return wrc;
@@ -391,7 +392,8 @@ static int64_t decompress_frame(zxg_ctx* g, const uint8_t* src, size_t src_size,
         if (!status) { ret = ZXC_ERROR_MEMORY; goto out; }
         const uint64_t src_lo = w.jobs[0].src_off;
         const uint64_t src_hi = w.jobs[n_fit - 1].src_off + w.jobs[n_fit - 1].src_len;
-        if (produced >= ((uint64_t)32 << 20) && zxg_host_pinned(src) && zxg_host_pinned(dst)) {
+        const int overlap = (const uint8_t*)src < dst + dst_capacity && dst < (const uint8_t*)src + src_size;
+        if (!overlap && produced >= ((uint64_t)32 << 20) && zxg_host_pinned(src) && zxg_host_pinned(dst)) {
             /* page-locked caller buffers: overlap H2D, decode and D2H chunk by chunk */
             const int prc = zxg_decode_pipelined(g, src, src_lo, src_hi, dst, produced, w.jobs, (uint32_t)n_fit, status,
                                                  dict, (uint32_t)dict_size, dict_huf, w.block_size, verify);
@@ -504,7 +506,8 @@ int64_t zxc_decompress_inplace(void* buffer, const size_t buffer_capacity, const
     const int rc = inplace_probe(comp, comp_size, &d, &m);
     if (rc != ZXC_OK) return rc;
     if (d > buffer_capacity || buffer_capacity - d < m) return ZXC_ERROR_DST_TOO_SMALL;
-    /* the whole frame is on the device before the first byte comes back */
+    /* source and destination overlap: decompress_frame then takes the staged path, where the whole
+     * frame is on the device before the first decoded byte comes back */
     return decompress_entry(NULL, comp, comp_size, buf, buffer_capacity, opts);
 }
 
@@ -522,6 +525,7 @@ static int64_t decode_one_block(zxc_dctx* dctx, const void* src, size_t src_size
     const size_t dict_size = (opts && opts->dict) ? opts->dict_size : 0;
     const uint8_t* dict_huf = (opts && opts->dict) ? (const uint8_t*)opts->dict_huf : NULL;
     const int verify = opts ? opts->checksum_enabled : 0;
+    if (dict_size > ZXC_DICT_SIZE_MAX) return ZXC_ERROR_DICT_TOO_LARGE;
     uint8_t* d_in = (uint8_t*)zxg_buffer(g, ZXG_BUF_IN, src_size + 16);
     uint8_t* d_out = (uint8_t*)zxg_buffer(g, ZXG_BUF_OUT, dst_capacity + 16);
     if (!d_in || !d_out) return ZXC_ERROR_MEMORY;
@@ -553,8 +557,8 @@ int64_t zxc_decompress_block_safe(zxc_dctx* dctx, const void* src, const size_t 
 }
 
 /* ------------------------------------------------------------------------- */
-/* encode entry points: the match-finder kernel is not in this build yet.    */
-/* They fail loudly instead of falling back to a CPU encoder.                */
+/* encode entry points: frame assembly on the host around zxg_encode_body     */
+/* (all levels encode on the GPU; without a device they fail loudly).        */
 /* ------------------------------------------------------------------------- */
 static int64_t compress_frame(zxg_ctx* g, const uint8_t* src, size_t src_size, uint8_t* dst, size_t dst_capacity,
                               int level, size_t block_size, int checksum, int seekable, const uint8_t* dict,
@@ -738,20 +742,26 @@ uint32_t zxc_seekable_get_block_decomp_size(const zxc_seekable* s, const uint32_
     return (s && i < s->tab.num_blocks) ? expected_block_bytes(s->tab.total, s->tab.block_size, i) : 0;
 }
 
+/* zxc_seekable.c:1144-1174: arguments are validated before the installed dictionary is touched, so a
+ * rejected call (NULL / empty, too large, id mismatch) leaves the handle as it was. */
 int zxc_seekable_set_dict(zxc_seekable* s, const void* dict, size_t dict_size, const void* dict_huf) {
-    if (!s) return ZXC_ERROR_NULL_INPUT;
-    free(s->dict);
-    s->dict = NULL;
-    s->dict_size = 0;
-    s->has_dict_huf = 0;
-    if (!dict || dict_size == 0) return ZXC_OK;
+    if (!s || !dict || dict_size == 0) return ZXC_ERROR_NULL_INPUT;
     if (dict_size > ZXC_DICT_SIZE_MAX) return ZXC_ERROR_DICT_TOO_LARGE;
     if (s->tab.dict_id != 0 && zxc_dict_id(dict, dict_size, dict_huf) != s->tab.dict_id)
         return ZXC_ERROR_DICT_MISMATCH;
-    s->dict = (uint8_t*)malloc(dict_size);
-    if (!s->dict) return ZXC_ERROR_MEMORY;
-    memcpy(s->dict, dict, dict_size);
+    uint8_t* copy = (uint8_t*)malloc(dict_size);
+    if (!copy) {
+        free(s->dict); /* the reference drops the old dictionary before it allocates (:1152-1158) */
+        s->dict = NULL;
+        s->dict_size = 0;
+        s->has_dict_huf = 0;
+        return ZXC_ERROR_MEMORY;
+    }
+    memcpy(copy, dict, dict_size);
+    free(s->dict);
+    s->dict = copy;
     s->dict_size = dict_size;
+    s->has_dict_huf = 0;
     if (dict_huf) {
         memcpy(s->dict_huf, dict_huf, ZXC_HUF_TABLE_SIZE);
         s->has_dict_huf = 1;

@@ -44,6 +44,8 @@ typedef int32_t i32;
 #define BT_EOF 255
 
 #define FLAG_VERIFY 1u
+#define FLAG_DEFERRED 2u /* only jobs whose status says D2_DEFER (left over by zxc_decode2_kernel) */
+#define D2_DEFER_STATUS ((i32)0x80000000)
 
 struct DecodeParams {
     const u8* src;
@@ -59,6 +61,9 @@ struct DecodeParams {
     u32 scratch_stride;
     u32 flags;
     u32 block_cap; /* largest decoded block size of this launch: sizes the per-warp scratch regions */
+    const u32* defer_list; /* FLAG_DEFERRED: job indices left over by zxc_decode2_kernel ... */
+    const u32* defer_count; /* ... how many; more than defer_cap means "scan the status array instead" */
+    u32 defer_cap;
 };
 
 /* ------------------------------------------------------------------------- */
@@ -84,7 +89,10 @@ __device__ __forceinline__ u32 warp_incl_scan(u32 v, u32 lane) {
 /* per-warp scratch layout (bytes), a function of the launch's block_cap */
 __host__ __device__ __forceinline__ u32 scr_lit_cap(u32 bs) { return (bs + 255u) & ~255u; }
 __host__ __device__ __forceinline__ u32 scr_tok_cap(u32 bs) { return (bs / 4u + 64u + 255u) & ~255u; }
-__host__ __device__ __forceinline__ u32 scr_cum_cap(u32 bs) { return (bs + 4096u + 255u) & ~255u; }
+/* rank words of the PivCo decode, worst case: HUF_MAXLEN (11) bitmap levels over every literal + one per node */
+__host__ __device__ __forceinline__ u32 scr_cum_cap(u32 bs) {
+    return (11u * (scr_lit_cap(bs) / 8u) + 4u * 512u + 255u) & ~255u;
+}
 __host__ __device__ __forceinline__ u32 scr_stride(u32 bs) {
     return 256u + scr_lit_cap(bs) + scr_tok_cap(bs) + (u32)HUF_WORK_BYTES + scr_cum_cap(bs);
 }
@@ -245,6 +253,7 @@ __device__ int parse_sections(const u8* pay, u32 comp, bool ghi, u32 cap, const 
     u8* tok_buf = scratch + scratch_cap;
     HufWork* hw = reinterpret_cast<HufWork*>(tok_buf + scr_tok_cap(block_cap));
     u32* cum = reinterpret_cast<u32*>(reinterpret_cast<u8*>(hw) + HUF_WORK_BYTES);
+    const u32 cum_words = scr_cum_cap(block_cap) / 4u;
     if (comp < 12) return ZXC_ERROR_BAD_HEADER;
     const u32 n_seq = ld32(pay), n_lit = ld32(pay + 4);
     const u32 enc_lit = pay[8], enc_tok = pay[9], enc_off = pay[11];
@@ -273,9 +282,9 @@ __device__ int parse_sections(const u8* pay, u32 comp, bool ghi, u32 cap, const 
                 int rc;
                 if (enc_lit == 2) {
                     if (lit_comp < 128) return ZXC_ERROR_CORRUPT_DATA;
-                    rc = pivco_decode(p_data, p_data + 128, lit_comp - 128, scratch, n_lit, hw, cum, lane);
+                    rc = pivco_decode(p_data, p_data + 128, lit_comp - 128, scratch, n_lit, hw, cum, cum_words, lane);
                 } else {
-                    rc = pivco_decode(dict_huf, p_data, lit_comp, scratch, n_lit, hw, cum, lane);
+                    rc = pivco_decode(dict_huf, p_data, lit_comp, scratch, n_lit, hw, cum, cum_words, lane);
                 }
                 if (rc != ZXC_OK) return rc;
                 __syncwarp();
@@ -315,7 +324,7 @@ __device__ int parse_sections(const u8* pay, u32 comp, bool ghi, u32 cap, const 
         if (enc_tok == 2) { /* level 7: Huffman-coded tokens (:1019-1022) */
             if (n_seq + 32u > scr_tok_cap(block_cap) || tok_comp < 128) return ZXC_ERROR_CORRUPT_DATA;
             if (n_seq) {
-                const int rc = pivco_decode(S.tok, S.tok + 128, tok_comp - 128, tok_buf, n_seq, hw, cum, lane);
+                const int rc = pivco_decode(S.tok, S.tok + 128, tok_comp - 128, tok_buf, n_seq, hw, cum, cum_words, lane);
                 if (rc != ZXC_OK) return rc;
                 __syncwarp();
             }
@@ -815,6 +824,41 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) zxc_decode_kernel(co
     const u32 gwarp = blockIdx.x * WARPS_PER_CTA + wic;
     u8* scratch = P.scratch + (size_t)gwarp * P.scratch_stride + 256; /* lead-in: word loads may start below */
     u8* ring = smem + (size_t)wic * RING_BYTES;
+    if (P.flags & FLAG_DEFERRED) {
+        const u32 n_def = *P.defer_count;
+        if (n_def <= P.defer_cap) { /* the listed jobs, one per claim */
+            for (;;) {
+                unsigned long long k = 0;
+                if (lane == 0) k = atomicAdd(P.counter, 1ull);
+                k = __shfl_sync(FULL, k, 0);
+                if (k >= n_def) break;
+                const u32 j = P.defer_list[k];
+                const zxc_b200_job_t job = P.jobs[j];
+                const int r = decode_job(P, job, scratch, ring, lane);
+                __syncwarp();
+                if (lane == 0) P.status[j] = r;
+            }
+            return;
+        }
+        /* list overflow: 32 status words per claim, the warp decodes the jobs still marked deferred */
+        for (;;) {
+            unsigned long long b = 0;
+            if (lane == 0) b = atomicAdd(P.counter, 32ull);
+            b = __shfl_sync(FULL, b, 0);
+            if (b >= P.n_jobs) break;
+            const unsigned long long jj = b + lane;
+            u32 m = __ballot_sync(FULL, jj < P.n_jobs && P.status[jj] == D2_DEFER_STATUS);
+            while (m) {
+                const unsigned long long j = b + (u32)(__ffs(m) - 1);
+                m &= m - 1;
+                const zxc_b200_job_t job = P.jobs[j];
+                const int r = decode_job(P, job, scratch, ring, lane);
+                __syncwarp();
+                if (lane == 0) P.status[j] = r;
+            }
+        }
+        return;
+    }
     for (;;) {
         unsigned long long j = 0;
         if (lane == 0) j = atomicAdd(P.counter, 1ull);

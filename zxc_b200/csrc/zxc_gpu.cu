@@ -1,22 +1,15 @@
 /*
- * zxc_gpu.cu -- sm_100a kernels and the thin extern "C" shim behind libzxc.
+ * zxc_gpu.cu -- the single CUDA translation unit behind libzxc: kernels (included .cuh files) and
+ * the thin extern "C" shim the host C code calls (zxc_gpu.h) -- device bring-up, contexts, staging
+ * copies, launches.
  *
- * Decode: one warp per independent block.  A
- * warp takes a batch of 32 sequences at a time, lane = sequence:
- *   1. token / offset unpack               (GLO zxc_decompress.c:626-694, GHI :701-727)
- *   2. escape resolution over the extras   (varint, :51-88) -- the k escapes of
- *      the batch are walked once, uniformly, each lane keeps the value(s) whose
- *      ordinal (ballot + popc) is its own
- *   3. warp prefix sums -> literal source offset and output offset per lane
- *   4. bounds / offset validation, first failing lane = first failing sequence
- *   5. literal copies (independent), then match copies in dependency rounds:
- *      a match is ready when its source ends below the lowest pending match
- *      destination; long runs are copied by the whole warp, overlap (off < ml)
- *      is resolved with the period-`off` index instead of the reference's
- *      shuffle tables (:197-413).
- * Output is written exactly (no wild-copy overshoot), so none of the
- * reference's PAD/TAIL_PAD slack is needed on the destination; the wire-level
- * 32-byte literal slack rule stays normative (:1003).
+ * Decode launches (launch_decode below):
+ *   zxc_decode2_kernel  (zxc_decode2.cuh) one CTA per block of <= 64 KiB, window in shared memory,
+ *                       cp.async.bulk in and out; takes GLO / GHI blocks with raw sections and RAW blocks
+ *   zxc_decode_kernel   (zxc_decode.cuh)  one warp per block, any block size / section encoding;
+ *                       runs second over whatever the first kernel deferred, or alone for block
+ *                       sizes above 64 KiB and for checksum-verifying decodes
+ * Encode: zxc_encode.cuh (levels 1-5), zxc_encode_opt.cuh (levels 6-7).
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -29,6 +22,7 @@
 #include "zxc_gpu.h"
 
 #include "zxc_decode.cuh"
+#include "zxc_decode2.cuh"
 #include "zxc_encode.cuh"
 
 /* ========================================================================= */
@@ -299,12 +293,62 @@ static int grid_for(u32 n_jobs) {
 /* per-warp scratch for expanded literal sections; 256 bytes of lead-in so word loads may start below it */
 static u32 scratch_stride_for(u32 block_size) { return scr_stride(block_size); }
 
+/* ---- block-cooperative kernel: launch geometry by block size ---------------------------------- */
+struct D2Config {
+    u32 win, gap, rcap, threads, smem, ctas_per_sm, spill_stride;
+};
+static int d2_enabled(void) {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("ZXC_B200_DECODE_V2");
+        cached = (e && e[0] == '0') ? 0 : 1;
+    }
+    return cached;
+}
+/* 1 when blocks of `block_size` decoded bytes go through zxc_decode2_kernel */
+static int d2_config(u32 block_size, D2Config* c) {
+    if (!d2_enabled() || block_size == 0 || block_size > Z2_WIN_MAX) return 0;
+    const u32 win = (block_size + Z2_GROUP - 1) & ~(Z2_GROUP - 1);
+    const u32 gap = win < 4096u ? win : 4096u;
+    const u32 nseq_max = block_size / 5u + 16u + 4u; /* zxc_common.c:142-144 */
+    const u32 fixed = d2_off_rec(win, gap) + 4u * 8u;
+    const u32 sm_total = 233472u; /* 228 KB per SM, 1 KB reserved per resident CTA */
+    u32 n = sm_total / (fixed + nseq_max * 8u + 1024u);
+    u32 rcap = nseq_max, spill = 0;
+    if (n < 2) { /* two blocks per SM: the tail of very long sequence lists lives in global memory */
+        n = 2;
+        rcap = (sm_total / 2u - 1024u - fixed) / 8u;
+        spill = nseq_max + 4u;
+    }
+    const u32 threads = win >= 32768u ? 256u : win >= 16384u ? 128u : 64u;
+    if (n > 32u) n = 32u;
+    if (n * threads > 2048u) n = 2048u / threads;
+    c->win = win;
+    c->gap = gap;
+    c->rcap = rcap;
+    c->threads = threads;
+    c->smem = d2_smem_bytes(win, gap, rcap);
+    c->ctas_per_sm = n;
+    c->spill_stride = spill;
+    return 1;
+}
+static size_t d2_spill_bytes(const D2Config* c) {
+    return (size_t)(g_sm_count > 0 ? g_sm_count : 148) * c->ctas_per_sm * c->spill_stride * sizeof(z2_rec_t);
+}
+
+#define SCRATCH_TAIL (sizeof(unsigned long long) * 4)
+#define DEFER_CAP (1u << 16) /* listed deferred jobs; beyond that the second launch scans the status array */
+
 extern "C" size_t zxc_b200_decode_scratch_size(uint32_t block_size) {
     if (zxg_init() != ZXC_OK) return 0;
     const size_t warps = (size_t)g_sm_count * CTAS_PER_SM * WARPS_PER_CTA;
-    return warps * scratch_stride_for(block_size) + sizeof(unsigned long long) * 4;
+    size_t n = warps * scratch_stride_for(block_size);
+    D2Config c;
+    if (d2_config(block_size, &c)) n += d2_spill_bytes(&c) + 256 + (size_t)DEFER_CAP * 4 + 256;
+    return n + SCRATCH_TAIL;
 }
 
+/* d_counter: two 64-bit work counters (zeroed here) */
 static int launch_decode(const void* d_src, void* d_dst, const zxc_b200_job_t* d_jobs, u32 n_jobs,
                          i32* d_status, const void* d_dict, u32 dict_size, const void* d_dict_huf,
                          void* d_scratch, size_t scratch_size, u32 block_size, int verify,
@@ -324,12 +368,73 @@ static int launch_decode(const void* d_src, void* d_dst, const zxc_b200_job_t* d
     P.scratch_stride = scratch_stride_for(block_size);
     P.flags = verify ? FLAG_VERIFY : 0;
     P.block_cap = block_size;
+    P.defer_list = NULL;
+    P.defer_count = NULL;
+    P.defer_cap = 0;
     const int grid = grid_for(n_jobs);
-    if ((size_t)grid * WARPS_PER_CTA * P.scratch_stride > scratch_size) return ZXC_ERROR_MEMORY;
-    if (cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st) != cudaSuccess) return ZXC_B200_ERROR_CUDA;
+    const size_t warp_scratch = (size_t)grid * WARPS_PER_CTA * P.scratch_stride;
+    if (warp_scratch > scratch_size) return ZXC_ERROR_MEMORY;
+    if (cudaMemsetAsync(d_counter, 0, 3 * sizeof(unsigned long long), st) != cudaSuccess) return ZXC_B200_ERROR_CUDA;
+    D2Config c;
+    if (!verify && d2_config(block_size, &c)) {
+        /* launch 1: one CTA per block, window in shared memory; launch 2: whatever it deferred */
+        static int attr_done_smem = 0;
+        if (attr_done_smem < (int)c.smem) {
+            if (cudaFuncSetAttribute(zxc_decode2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 233472 - 1024) !=
+                cudaSuccess)
+                return ZXC_B200_ERROR_CUDA;
+            attr_done_smem = 233472;
+        }
+        Decode2Params Q;
+        Q.src = P.src;
+        Q.dst = P.dst;
+        Q.jobs = d_jobs;
+        Q.status = d_status;
+        Q.dict = P.dict;
+        Q.counter = d_counter;
+        Q.spill = NULL;
+        Q.n_jobs = n_jobs;
+        Q.dict_size = P.dict_size;
+        Q.win = c.win;
+        Q.gap = c.gap;
+        Q.rcap = c.rcap;
+        Q.spill_stride = c.spill_stride;
+        const u32 resident = (u32)(g_sm_count > 0 ? g_sm_count : 148) * c.ctas_per_sm;
+        const u32 grid2 = n_jobs < resident ? n_jobs : resident;
+        size_t off = (warp_scratch + 255) & ~(size_t)255;
+        if (c.spill_stride) {
+            if (off + (size_t)grid2 * c.spill_stride * sizeof(z2_rec_t) > scratch_size) return ZXC_ERROR_MEMORY;
+            Q.spill = (z2_rec_t*)((u8*)d_scratch + off);
+            off = (off + d2_spill_bytes(&c) + 255) & ~(size_t)255;
+        }
+        /* deferred-job list behind the spill area; its counter is the third work counter */
+        Q.defer_count = (u32*)(d_counter + 2);
+        Q.defer_cap = off + (size_t)DEFER_CAP * 4 <= scratch_size ? DEFER_CAP : 0u;
+        Q.defer_list = (u32*)((u8*)d_scratch + off);
+        P.defer_list = Q.defer_list;
+        P.defer_count = Q.defer_count;
+        P.defer_cap = Q.defer_cap;
+        zxc_decode2_kernel<<<grid2, c.threads, c.smem, st>>>(Q);
+        __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
+        if (cudaGetLastError() != cudaSuccess) return ZXC_B200_ERROR_CUDA;
+        P.flags |= FLAG_DEFERRED;
+        P.counter = d_counter + 1;
+    }
     zxc_decode_kernel<<<grid, CTA_THREADS, DECODE_SMEM_BYTES, st>>>(P);
     __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
     return cudaGetLastError() == cudaSuccess ? ZXC_OK : ZXC_B200_ERROR_CUDA;
+}
+
+/* device scratch one launch over n_jobs blocks needs (without the counter tail) */
+static size_t launch_scratch_bytes(u32 n_jobs, u32 block_size) {
+    size_t n = (size_t)grid_for(n_jobs) * WARPS_PER_CTA * scratch_stride_for(block_size);
+    D2Config c;
+    if (d2_config(block_size, &c)) {
+        n = (n + 255) & ~(size_t)255;
+        if (c.spill_stride) n = (n + d2_spill_bytes(&c) + 255) & ~(size_t)255;
+        n += (size_t)DEFER_CAP * 4 + 256;
+    }
+    return n;
 }
 
 extern "C" int zxc_b200_decode_blocks(const void* d_src, void* d_dst, const zxc_b200_job_t* d_jobs,
@@ -340,9 +445,9 @@ extern "C" int zxc_b200_decode_blocks(const void* d_src, void* d_dst, const zxc_
     const int rc = zxg_init();
     if (rc != ZXC_OK) return rc;
     if (!d_src || !d_dst || !d_jobs || !d_status || !d_scratch) return ZXC_ERROR_NULL_INPUT;
-    if (scratch_size < 4 * sizeof(unsigned long long)) return ZXC_ERROR_MEMORY;
-    /* the work counter lives in the last 32 bytes of the caller's scratch */
-    const size_t usable = (scratch_size - 4 * sizeof(unsigned long long)) & ~(size_t)7;
+    if (scratch_size < SCRATCH_TAIL) return ZXC_ERROR_MEMORY;
+    /* the work counters live in the last 32 bytes of the caller's scratch */
+    const size_t usable = (scratch_size - SCRATCH_TAIL) & ~(size_t)7;
     unsigned long long* counter = (unsigned long long*)((u8*)d_scratch + usable);
     return launch_decode(d_src, d_dst, d_jobs, n_jobs, d_status, d_dict, dict_size, d_dict_huf,
                          d_scratch, usable, block_size, verify_checksums, counter, (cudaStream_t)stream);
@@ -383,8 +488,7 @@ extern "C" int zxg_decode_jobs(zxg_ctx* c, const void* d_src, void* d_dst, const
     if (n_jobs == 0) return ZXC_OK;
     zxc_b200_job_t* d_jobs = (zxc_b200_job_t*)zxg_buffer(c, ZXG_BUF_JOBS, (size_t)n_jobs * sizeof(zxc_b200_job_t));
     i32* d_status = (i32*)zxg_buffer(c, ZXG_BUF_STATUS, (size_t)n_jobs * sizeof(i32));
-    const size_t warps = (size_t)grid_for(n_jobs) * WARPS_PER_CTA;
-    const size_t scratch_size = warps * scratch_stride_for(block_size);
+    const size_t scratch_size = launch_scratch_bytes(n_jobs, block_size);
     void* d_scratch = zxg_buffer(c, ZXG_BUF_SCRATCH, scratch_size);
     if (!d_jobs || !d_status || !d_scratch) return ZXC_ERROR_MEMORY;
     u8* d_dict = NULL;
@@ -433,8 +537,7 @@ extern "C" int zxg_decode_pipelined(zxg_ctx* c, const uint8_t* h_src, uint64_t s
     u8* d_out = (u8*)zxg_buffer(c, ZXG_BUF_OUT, (size_t)produced + 16);
     zxc_b200_job_t* d_jobs = (zxc_b200_job_t*)zxg_buffer(c, ZXG_BUF_JOBS, (size_t)n_jobs * sizeof(zxc_b200_job_t));
     i32* d_status = (i32*)zxg_buffer(c, ZXG_BUF_STATUS, (size_t)n_jobs * sizeof(i32));
-    const size_t warps = (size_t)grid_for(n_jobs) * WARPS_PER_CTA;
-    const size_t scratch_size = warps * scratch_stride_for(block_size);
+    const size_t scratch_size = launch_scratch_bytes(n_jobs, block_size);
     void* d_scratch = zxg_buffer(c, ZXG_BUF_SCRATCH, scratch_size);
     if (!d_in || !d_out || !d_jobs || !d_status || !d_scratch) return ZXC_ERROR_MEMORY;
     u8* d_dict = NULL;

@@ -42,9 +42,12 @@ __device__ __forceinline__ u32 huf_bits32(const u8* run, u32 word) { /* 32 run b
     return (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24);
 }
 
-/* Decodes n symbols.  lens128: 128 packed nibbles; runs/rsz: the run area; cum: >= rsz/4 + 600 words. */
+/* Decodes n symbols.  lens128: 128 packed nibbles; runs/rsz: the run area; cum: cum_words rank words.
+ * Every symbol sits in at most one bitmap node per level, so a well-formed section needs at most
+ * HUF_MAXLEN * n / 32 + HUF_MAXNODES rank words (scr_cum_cap); a crafted one that asks for more is
+ * rejected before the table is written. */
 __device__ __noinline__ int pivco_decode(const u8* lens128, const u8* runs, u32 rsz, u8* out, u32 n, HufWork* W,
-                                         u32* cum, u32 lane) {
+                                         u32* cum, u32 cum_words, u32 lane) {
     /* ---- code lengths: validate, count, Kraft (zxc_huffman.c:1055-1064) ---- */
     u32 my_len[8];
     u32 kraft = 0, present = 0;
@@ -189,6 +192,7 @@ __device__ __noinline__ int pivco_decode(const u8* lens128, const u8* runs, u32 
         if (bytes > rsz - roff) return ZXC_ERROR_CORRUPT_DATA;
         const u8* run = runs + roff;
         const u32 words = (c + 31) >> 5;
+        if (words > cum_words - coff) return ZXC_ERROR_CORRUPT_DATA;
         u32 ones = 0;
         for (u32 w0 = 0; w0 < words; w0 += 32) {
             const u32 wi = w0 + lane;

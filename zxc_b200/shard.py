@@ -51,6 +51,51 @@ def rebase_jobs(jobs, b0, b1, src_lo, dst_lo):
     return out
 
 
+CHUNK = 1 << 30  # bytes per point-to-point message (keeps element counts far below 2^31)
+
+
+def _pieces(t):
+    return [t[o:o + CHUNK] for o in range(0, t.numel(), CHUNK)]
+
+
+def scatter_ranges_p2p(frame, ranges, dist, device, src_rank=0):
+    """Batched variant for NCCL: `ranges[r] = (lo, hi)` byte range of `frame` (held by src_rank) for rank r.
+    All sends are posted together (one ncclGroup), so the root's NVLink egress is shared by all peers."""
+    import torch
+    rank = dist.get_rank()
+    lo, hi = ranges[rank]
+    mine = torch.empty(hi - lo, dtype=torch.uint8, device=device)
+    ops = []
+    if rank == src_rank:
+        for r, (rlo, rhi) in enumerate(ranges):
+            if r == src_rank:
+                mine.copy_(frame[rlo:rhi])
+            else:
+                ops += [dist.P2POp(dist.isend, pc, r) for pc in _pieces(frame[rlo:rhi])]
+    else:
+        ops += [dist.P2POp(dist.irecv, pc, src_rank) for pc in _pieces(mine)]
+    if ops:
+        for q in dist.batch_isend_irecv(ops):
+            q.wait()
+    return mine
+
+
+def gather_ranges_p2p(decoded, out, ranges, dist, dst_rank=0):
+    """Inverse exchange into `out` (on dst_rank; its own range is expected to be in place already):
+    every other rank sends `decoded` into out[lo:hi]."""
+    rank = dist.get_rank()
+    ops = []
+    if rank == dst_rank:
+        for r, (rlo, rhi) in enumerate(ranges):
+            if r != dst_rank:
+                ops += [dist.P2POp(dist.irecv, pc, r) for pc in _pieces(out[rlo:rhi])]
+    else:
+        ops += [dist.P2POp(dist.isend, pc, dst_rank) for pc in _pieces(decoded)]
+    if ops:
+        for q in dist.batch_isend_irecv(ops):
+            q.wait()
+
+
 def scatter_ranges(frame, comp_sizes, block_size, total, dist, device="cpu", src_rank=0):
     """Rank `src_rank` holds `frame` (uint8 tensor); every rank returns (its compressed slice, b0, b1).
 
