@@ -44,7 +44,9 @@ step(); torch.cuda.synchronize()
 stt = d_status.cpu().numpy()
 jv = jobs.view(np.dtype([("src_off", "<u8"), ("dst_off", "<u8"), ("src_len", "<u4"), ("dst_cap", "<u4")]))
 bad = np.nonzero(stt != jv["dst_cap"].astype(np.int64))[0]
-print("blocks", nb, "bad status", bad.size, stt[bad[:8]] if bad.size else "")
+usable = (ss - 32) & ~7
+tail = d_scr[usable:usable + 32].cpu().numpy().view(np.uint32)
+print("blocks", nb, "bad status", bad.size, stt[bad[:8]] if bad.size else "", "deferred by the block-cooperative kernel:", int(tail[4]))
 got = d_dst.cpu().numpy()
 if not np.array_equal(got, data):
     w = np.nonzero(got != data)[0]

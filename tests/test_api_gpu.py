@@ -37,7 +37,7 @@ def make_reader(frame, calls):
 
 
 def test_reader_backed_handle(prod, ref):
-    data = zc.silesia_shaped(24 << 20, seed=4)
+    data = zc.silesia_shaped(80 << 20, seed=4)  # > 32 MiB: the staged reader pipeline
     frame = zc.compress_ref_mt(ref, data, level=3, block_size=65536)
     calls = []
     rd, keep = make_reader(frame, calls)

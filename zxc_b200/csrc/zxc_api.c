@@ -403,6 +403,16 @@ static int64_t decompress_frame(zxg_ctx* g, const uint8_t* src, size_t src_size,
             if (pf < 0) { ret = pf; goto out; }
             goto decoded;
         }
+        if (!overlap && produced >= ((uint64_t)32 << 20)) {
+            /* ordinary (pageable) caller memory: the same overlap through pinned bounce buffers and the copy pool */
+            const int prc = zxg_decode_staged(g, src, NULL, NULL, src_lo, src_hi, dst, 0, produced, w.jobs, (uint32_t)n_fit,
+                                              status, dict, (uint32_t)dict_size, dict_huf, w.block_size, verify);
+            if (prc != ZXC_OK) { ret = prc; goto out; }
+            int mm = 0;
+            const int64_t pf = first_failure(status, w.jobs, n_fit, &mm);
+            if (pf < 0) { ret = pf; goto out; }
+            goto decoded;
+        }
         uint8_t* d_in = (uint8_t*)zxg_buffer(g, ZXG_BUF_IN, (size_t)(src_hi - src_lo) + 16);
         uint8_t* d_out = (uint8_t*)zxg_buffer(g, ZXG_BUF_OUT, (size_t)produced + 16);
         if (!d_in || !d_out) { ret = ZXC_ERROR_MEMORY; goto out; }
@@ -799,15 +809,33 @@ static int64_t seekable_range(zxc_seekable* s, void* dst, size_t dst_capacity, u
         jobs[i].dst_cap = expected_block_bytes(s->tab.total, bs, b0 + i);
         out_bytes = jobs[i].dst_off + jobs[i].dst_cap;
     }
+    int rc;
+    if (s->src && c_hi > s->src_size) { ret = ZXC_ERROR_SRC_TOO_SMALL; goto out; }
+    if (out_bytes >= ((uint64_t)32 << 20)) {
+        /* large range: H2D, decode and D2H overlapped chunk by chunk.  Job source offsets become absolute frame
+         * offsets; decoded coordinates start at the first covered block. */
+        for (uint32_t i = 0; i < nb; i++) jobs[i].src_off += c_lo;
+        const uint64_t clip_lo = offset - out_lo, clip_hi = clip_lo + len;
+        const int aligned = clip_lo == 0 && clip_hi == out_bytes;
+        if (s->src && aligned && zxg_host_pinned(s->src) && zxg_host_pinned(dst))
+            rc = zxg_decode_pipelined(g, s->src, c_lo, c_hi, (uint8_t*)dst, out_bytes, jobs, nb, st, s->dict,
+                                      (uint32_t)s->dict_size, s->has_dict_huf ? s->dict_huf : NULL, bs, 0);
+        else
+            rc = zxg_decode_staged(g, s->src, s->src ? NULL : seekable_fetch, s, c_lo, c_hi, (uint8_t*)dst, clip_lo, clip_hi,
+                                   jobs, nb, st, s->dict, (uint32_t)s->dict_size, s->has_dict_huf ? s->dict_huf : NULL, bs, 0);
+        if (rc != ZXC_OK) { ret = rc; goto out; }
+        int mm = 0;
+        const int64_t pf = first_failure(st, jobs, nb, &mm);
+        ret = pf < 0 ? pf : (int64_t)len;
+        goto out;
+    }
     uint8_t* d_in = (uint8_t*)zxg_buffer(g, ZXG_BUF_IN, (size_t)(c_hi - c_lo) + 16);
     uint8_t* d_out = (uint8_t*)zxg_buffer(g, ZXG_BUF_OUT, (size_t)out_bytes + 16);
     if (!d_in || !d_out) { ret = ZXC_ERROR_MEMORY; goto out; }
-    int rc;
     if (s->src) {
-        if (c_hi > s->src_size) { ret = ZXC_ERROR_SRC_TOO_SMALL; goto out; }
         rc = zxg_h2d(g, d_in, s->src + c_lo, (size_t)(c_hi - c_lo));
     } else {
-        /* reader mode: pull the compressed span through a host bounce, 16 MiB at a time */
+        /* reader mode, small range: pull the compressed span through a host bounce */
         const size_t chunk = (size_t)16 << 20;
         uint8_t* bounce = (uint8_t*)malloc(c_hi - c_lo < chunk ? (size_t)(c_hi - c_lo) : chunk);
         rc = bounce ? ZXC_OK : ZXC_ERROR_MEMORY;

@@ -44,6 +44,8 @@ typedef int32_t i32;
 #define BT_EOF 255
 
 #define FLAG_VERIFY 1u
+#define FLAG_UNITS_ON 4u
+#define FLAG_UNITS_OFF 8u
 #define FLAG_DEFERRED 2u /* only jobs whose status says D2_DEFER (left over by zxc_decode2_kernel) */
 #define D2_DEFER_STATUS ((i32)0x80000000)
 
@@ -347,6 +349,8 @@ __device__ int parse_sections(const u8* pay, u32 comp, bool ghi, u32 cap, const 
     return ZXC_OK;
 }
 
+#include "zxc_decode_units.cuh"
+
 /* ------------------------------------------------------------------------- */
 /* output window: ring (recent) + global (flushed) + dictionary (negative)    */
 /* ------------------------------------------------------------------------- */
@@ -562,9 +566,10 @@ __device__ __forceinline__ void group4_copy_words(u8* ring, u32 m_items, u32 my_
 /* ------------------------------------------------------------------------- */
 /* GLO / GHI block body.  Returns decoded bytes or a negative zxc_error_t.    */
 /* ------------------------------------------------------------------------- */
+template <bool UNITS>
 __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 cap, const u8* dict,
                                u32 dict_size, const u8* dict_huf, u8* scratch, u32 scratch_cap, u8* ring,
-                               u32 lane) {
+                               u32 lane, u32 P_flags) {
     Sections S;
     const int prc = parse_sections(pay, comp, ghi, cap, dict_huf, scratch, scratch_cap, lane, S);
     if (prc != ZXC_OK) return prc;
@@ -573,6 +578,24 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
     const u8* offs = S.offs;
     const u8* ext = S.ext;
     const u32 ext_end = S.ext_end, n_lit_avail = S.n_lit_avail, n_seq = S.n_seq, enc_off = S.enc_off;
+
+    /* Output-centric body (zxc_decode_units.cuh) where it measured faster than the sequence-centric one below:
+     * dictionary decodes of small blocks (BASELINE configs[3]: 298 vs 152 GB/s on 4 KiB records) -- dictionary
+     * sources are plain 16-byte gathers there, byte paths here.  At 64 KiB blocks without a dictionary it is the
+     * slower one (156 vs 307 GB/s), see DESIGN.md.  The launch picks the kernel instance (launch_decode);
+     * ZXC_B200_UNITS=1 / 0 forces it on / off. */
+    (void)P_flags;
+    if (UNITS && cap <= 65536u) { /* its tables go where the scratch is idle */
+        u8* tok_buf = scratch + scr_lit_cap(scratch_cap);
+        u8* hw_area = tok_buf + scr_tok_cap(scratch_cap);
+        const bool scratch_busy = (lit == scratch) || (tok == tok_buf);
+        u8* tab = scratch_busy ? hw_area : scratch;
+        const u32 tab_bytes = scratch_busy ? (u32)HUF_WORK_BYTES + scr_cum_cap(scratch_cap)
+                                           : scr_stride(scratch_cap) - 256u;
+        const int r = decode_lz_units(lit, n_lit_avail, tok, offs, ext, ext_end, n_seq, enc_off, ghi, out, cap, dict,
+                                      dict_size, tab, tab_bytes, lane);
+        if (r != UW_NOT_TAKEN) return r;
+    }
 
     const u32 mask = RING_BYTES - 1;
     const u32 esc = ghi ? 255u : 15u;
@@ -789,6 +812,7 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
 }
 
 /* zxc_decompress_chunk_wrapper_body (zxc_decompress.c:1646-1695) for one job */
+template <bool UNITS>
 __device__ int decode_job(const DecodeParams& P, const zxc_b200_job_t& job, u8* scratch, u8* ring, u32 lane) {
     const u8* blk = P.src + job.src_off;
     u8* out = P.dst + job.dst_off;
@@ -804,8 +828,8 @@ __device__ int decode_job(const DecodeParams& P, const zxc_b200_job_t& job, u8* 
     switch (type) {
         case BT_GLO:
         case BT_GHI:
-            return decode_lz_block(data, comp, type == BT_GHI, out, job.dst_cap, P.dict, P.dict_size,
-                                   P.dict_huf, scratch, P.block_cap, ring, lane);
+            return decode_lz_block<UNITS>(data, comp, type == BT_GHI, out, job.dst_cap, P.dict, P.dict_size,
+                                   P.dict_huf, scratch, P.block_cap, ring, lane, P.flags);
         case BT_RAW:
             if (comp > job.dst_cap) return ZXC_ERROR_DST_TOO_SMALL;
             warp_copy(out, data, comp, lane);
@@ -817,6 +841,7 @@ __device__ int decode_job(const DecodeParams& P, const zxc_b200_job_t& job, u8* 
     }
 }
 
+template <bool UNITS, bool DEFERRED>
 __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) zxc_decode_kernel(const DecodeParams P) {
     extern __shared__ __align__(16) u8 smem[];
     const u32 lane = threadIdx.x & 31;
@@ -824,7 +849,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) zxc_decode_kernel(co
     const u32 gwarp = blockIdx.x * WARPS_PER_CTA + wic;
     u8* scratch = P.scratch + (size_t)gwarp * P.scratch_stride + 256; /* lead-in: word loads may start below */
     u8* ring = smem + (size_t)wic * RING_BYTES;
-    if (P.flags & FLAG_DEFERRED) {
+    if (DEFERRED) {
         const u32 n_def = *P.defer_count;
         if (n_def <= P.defer_cap) { /* the listed jobs, one per claim */
             for (;;) {
@@ -834,7 +859,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) zxc_decode_kernel(co
                 if (k >= n_def) break;
                 const u32 j = P.defer_list[k];
                 const zxc_b200_job_t job = P.jobs[j];
-                const int r = decode_job(P, job, scratch, ring, lane);
+                const int r = decode_job<UNITS>(P, job, scratch, ring, lane);
                 __syncwarp();
                 if (lane == 0) P.status[j] = r;
             }
@@ -852,7 +877,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) zxc_decode_kernel(co
                 const unsigned long long j = b + (u32)(__ffs(m) - 1);
                 m &= m - 1;
                 const zxc_b200_job_t job = P.jobs[j];
-                const int r = decode_job(P, job, scratch, ring, lane);
+                const int r = decode_job<UNITS>(P, job, scratch, ring, lane);
                 __syncwarp();
                 if (lane == 0) P.status[j] = r;
             }
@@ -865,7 +890,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) zxc_decode_kernel(co
         j = __shfl_sync(FULL, j, 0);
         if (j >= P.n_jobs) break;
         const zxc_b200_job_t job = P.jobs[j];
-        const int r = decode_job(P, job, scratch, ring, lane);
+        const int r = decode_job<UNITS>(P, job, scratch, ring, lane);
         __syncwarp();
         if (lane == 0) P.status[j] = r;
     }

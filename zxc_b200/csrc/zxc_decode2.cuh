@@ -47,6 +47,7 @@ struct Decode2Params {
     u32* defer_list; /* job indices this kernel left to the general kernel */
     u32* defer_count;
     u32 defer_cap;
+    unsigned long long* trace; /* development: 8 clock64() stamps per job, or NULL */
     u32 n_jobs;
     u32 dict_size;
     u32 win;  /* output window bytes: multiple of 512, <= 65536 */
@@ -60,8 +61,9 @@ struct Decode2Params {
 #define D2_OFF_CTRL 16u    /* u32[28] control words */
 #define D2_OFF_SCAN 128u   /* u64[40] scan scratch */
 #define D2_OFF_GIDX 448u   /* u16[136] first sequence of every group */
-#define D2_OFF_DM 768u     /* u32[512] per-row completion masks */
-#define D2_OFF_WIN 2816u   /* window: win + gap + 128 */
+#define D2_OFF_RC 768u     /* u32[16]: one bit per completed 128-byte row */
+#define D2_OFF_ROWBAR 896u /* u64[512]: one mbarrier per row, for warps that have nothing ready */
+#define D2_OFF_WIN 4992u   /* window: win + gap + 128 */
 __host__ __device__ __forceinline__ u32 d2_off_rec(u32 win, u32 gap) { return D2_OFF_WIN + win + gap + 128u; }
 __host__ __device__ __forceinline__ u32 d2_smem_bytes(u32 win, u32 gap, u32 rcap) {
     return d2_off_rec(win, gap) + (rcap + 4u) * 8u;
@@ -92,6 +94,9 @@ __device__ __forceinline__ void d2_mbar_wait(u32 bar, u32 parity) {
             : "memory");
     } while (!ok);
 }
+__device__ __forceinline__ void d2_mbar_arrive(u32 bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void d2_bulk_store(void* gdst, u32 ssrc, u32 bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes)
                  : "memory");
@@ -99,6 +104,15 @@ __device__ __forceinline__ void d2_bulk_store(void* gdst, u32 ssrc, u32 bytes) {
 }
 __device__ __forceinline__ void d2_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void d2_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+/* Completion masks are published with release semantics and read with acquire semantics at CTA scope.
+ * ptxas lowers ld.acquire.cta.shared to a plain LDS (shared loads of a thread are performed in order), so
+ * only the publishing side pays a MEMBAR.ALL.CTA. */
+__device__ __forceinline__ void d2_release_fence() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+__device__ __forceinline__ u32 d2_ld_acquire(const volatile u32* p) {
+    u32 v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((u32)__cvta_generic_to_shared(const_cast<u32*>(p))) : "memory");
+    return v;
+}
 __device__ __forceinline__ void d2_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void d2_prefetch_l2(const void* g, u32 bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g), "r"(bytes) : "memory");
@@ -127,16 +141,64 @@ __device__ __forceinline__ u32 d2_gather(const u8* win, i32 s) {
     const u32 w0 = wp[0], w1 = wp[1];
     return __byte_perm(w0, w1, 0x3210u + 0x1111u * ((u32)s & 3u));
 }
+/* Completion state as one warp sees it while it works on group `g4 / 4`:
+ *   lead   rows [0, lead) are complete (contiguous prefix of the row bitmap; a lower bound)
+ *   own    completion masks of the warp's own four rows (registers, identical in every lane)
+ * A source word is usable when its row is below `lead`, or it is one of the warp's own finished words. */
+struct D2Prog {
+    u32 lead, g4;
+    u32 own[Z2_ROWS];
+};
+__device__ __forceinline__ bool d2_word_ok(const D2Prog& S, u32 w) {
+    const u32 r = w >> 5;
+    if (r < S.lead) return true;
+    if (r < S.g4) return false;
+    const u32 q = r - S.g4;
+    const u32 m = q == 0 ? S.own[0] : q == 1 ? S.own[1] : q == 2 ? S.own[2] : S.own[3];
+    return ((m >> (w & 31u)) & 1u) != 0u;
+}
 /* are the words holding window bytes [s, s+4) complete? */
-__device__ __forceinline__ bool d2_ready(const volatile u32* dm, i32 s) {
+__device__ __forceinline__ bool d2_ready(const D2Prog& S, i32 s) {
     const u32 w0 = (u32)s >> 2, w1 = ((u32)s + 3u) >> 2;
-    const u32 m0 = dm[w0 >> 5], m1 = dm[w1 >> 5];
-    return (((m0 >> (w0 & 31u)) & (m1 >> (w1 & 31u))) & 1u) != 0u;
+    if ((w1 >> 5) < S.lead) return true;
+    return d2_word_ok(S, w0) && d2_word_ok(S, w1);
+}
+
+/* RLE literal section (zxc_decompress.c:906-978) expanded inside the window buffer: the compressed stream
+ * sits right-aligned at the end of the buffer, the literals grow from `wp` upwards behind the read cursor.
+ * Returns ZXC_OK, ZXC_ERROR_CORRUPT_DATA as the reference would, or 1 when a burst of run tokens would
+ * overrun bytes that have not been read yet (the block then goes to the general kernel). */
+__device__ int d2_rle_inplace(u8* buf, u32 rp, u32 rend, u32 wp, u32 wend, u32 lane) {
+    while (rp < rend && wp < wend) {
+        const u32 t = buf[rp++];
+        if (!(t & 0x80u)) {
+            const u32 len = t + 1u;
+            if (wend - wp < len || rend - rp < len) return ZXC_ERROR_CORRUPT_DATA;
+            if (wp > rp) return 1;
+            for (u32 c = 0; c < len; c += 32) { /* forward overlapping copy: destination at or below the source */
+                const u32 k = c + lane;
+                const u8 v = k < len ? buf[rp + k] : (u8)0;
+                __syncwarp();
+                if (k < len) buf[wp + k] = v;
+                __syncwarp();
+            }
+            wp += len;
+            rp += len;
+        } else {
+            const u32 len = (t & 0x7Fu) + 4u;
+            if (wend - wp < len || rp >= rend) return ZXC_ERROR_CORRUPT_DATA;
+            const u8 v = buf[rp++];
+            if (wp + len > rp) return 1;
+            for (u32 k = lane; k < len; k += 32) buf[wp + k] = v;
+            wp += len;
+        }
+        __syncwarp();
+    }
+    return wp == wend ? ZXC_OK : ZXC_ERROR_CORRUPT_DATA;
 }
 
 struct D2Block {
     u8* win;            /* window base (shared) */
-    volatile u32* dm;   /* row masks */
     const z2_rec_t* rs; /* records in shared memory */
     const z2_rec_t* rg; /* records in global memory (same indexing) */
     const u8* dict;
@@ -169,7 +231,7 @@ __device__ __forceinline__ void d2_seq_pair(const D2Block& B, u32 idx, z2_seq_t&
 
 /* byte-wise word (wrapped periods, off < 4, dictionary sources).  Returns false when a source
  * byte is not complete yet. */
-__device__ __noinline__ bool d2_slow_word(const D2Block& B, u32 idx, i32 p, u32& out) {
+__device__ __noinline__ bool d2_slow_word(const D2Block& B, const D2Prog S, u32 idx, i32 p, u32& out) {
     z2_seq_t c, n;
     d2_seq_pair(B, idx, c, n);
     u32 acc = 0;
@@ -187,9 +249,7 @@ __device__ __noinline__ bool d2_slow_word(const D2Block& B, u32 idx, i32 p, u32&
         } else if (s >= p) {
             v = (acc >> (8 * (s - p))) & 0xFFu;
         } else {
-            const u32 w = (u32)s >> 2;
-            if (!((B.dm[w >> 5] >> (w & 31u)) & 1u)) return false;
-            __threadfence_block();
+            if (!d2_word_ok(S, (u32)s >> 2)) return false;
             v = *reinterpret_cast<volatile u8*>(B.win + s);
         }
         acc |= v << (8 * b);
@@ -207,7 +267,8 @@ __global__ void __launch_bounds__(256, 2) zxc_decode2_kernel(const Decode2Params
     u32* scan32 = reinterpret_cast<u32*>(sm + D2_OFF_SCAN);
     u64* scan64 = reinterpret_cast<u64*>(sm + D2_OFF_SCAN);
     unsigned short* gidx = reinterpret_cast<unsigned short*>(sm + D2_OFF_GIDX);
-    u32* dmw = reinterpret_cast<u32*>(sm + D2_OFF_DM);
+    u32* rcw = reinterpret_cast<u32*>(sm + D2_OFF_RC);
+    const u32 rowbar = d2_saddr(sm + D2_OFF_ROWBAR);
     u8* win = sm + D2_OFF_WIN;
     z2_rec_t* recs = reinterpret_cast<z2_rec_t*>(sm + d2_off_rec(P.win, P.gap));
     z2_rec_t* recg = P.spill ? P.spill + (size_t)blockIdx.x * P.spill_stride : recs;
@@ -215,9 +276,11 @@ __global__ void __launch_bounds__(256, 2) zxc_decode2_kernel(const Decode2Params
     const u32 rec_room = P.spill ? P.spill_stride : P.rcap;
     const u32 bar = d2_saddr(sm + D2_OFF_MBAR);
     const u32 KGUARD = P.gap / Z2_GROUP;
-    u32 phase = 0;
+    const u32 rows_max = P.win / 128u;
+    u32 phase = 0, row_par = 0; /* parity of the load barrier / of the row barriers' current phase */
 
     if (tid == 0) d2_mbar_init(bar, 1);
+    for (u32 r = tid; r < rows_max; r += T) d2_mbar_init(rowbar + 8u * r, 1);
     __syncthreads();
 
     for (;;) {
@@ -226,10 +289,18 @@ __global__ void __launch_bounds__(256, 2) zxc_decode2_kernel(const Decode2Params
         __syncthreads();
         const u32 j = vctrl[C_JOB];
         if (j >= P.n_jobs) break;
+#define D2_STAMP(i) do { if (P.trace && tid == 0) P.trace[(size_t)j * 8 + (i)] = (unsigned long long)clock64(); } while (0)
+        D2_STAMP(0);
         const zxc_b200_job_t job = P.jobs[j];
         const u8* blk = P.src + job.src_off;
         u8* out = P.dst + job.dst_off;
         const u32 cap = job.dst_cap;
+        if (tid == 32 && j + gridDim.x < P.n_jobs) { /* pull the block a CTA will want one round from now into L2 */
+            const zxc_b200_job_t nj = P.jobs[j + gridDim.x];
+            const u8* nb = P.src + nj.src_off;
+            const u32 sh = (u32)(reinterpret_cast<uintptr_t>(nb) & 15u);
+            d2_prefetch_l2(nb - sh, (sh + nj.src_len + 15u) & ~15u);
+        }
 
         /* ---- header: anything unusual is left to the general kernel ---- */
         int verdict = 0; /* 0 = take it, 1 = raw copy, 2 = defer */
@@ -274,12 +345,13 @@ __global__ void __launch_bounds__(256, 2) zxc_decode2_kernel(const Decode2Params
                 ext_len = avail - (u32)consumed;
                 /* room: [S | values | RLE stream] below the staged literals */
                 const u32 lba = (P.win + P.gap - n_lit + 15u) & ~15u;
-                u64 low = (u64)s_bytes + 48 + 4ull * ext_len + 16;
-                if (rle) {
-                    rle_at = (u32)((low + 15) & ~15ull);
-                    low = (u64)rle_at + lit_comp + 48;
-                }
+                const u64 low = (u64)s_bytes + 48 + 4ull * ext_len + 16;
                 if (low > lba) verdict = 2;
+                if (rle) { /* compressed stream right-aligned at the end of the buffer (16-byte granules) */
+                    const u32 buf_end = P.win + P.gap + 128u;
+                    if ((u64)lit_comp + 64 + low > buf_end) verdict = 2;
+                    else rle_at = (buf_end - lit_comp - 32u) & ~15u;
+                }
             }
         }
         if (verdict == 2) {
@@ -337,26 +409,37 @@ __global__ void __launch_bounds__(256, 2) zxc_decode2_kernel(const Decode2Params
         /* control state while the copies fly */
         const u32 n_groups_max = (cap + Z2_GROUP - 1) / Z2_GROUP;
         for (u32 k = tid; k <= n_groups_max; k += T) gidx[k] = (unsigned short)n_seq;
-        for (u32 k = tid; k < n_groups_max * Z2_ROWS; k += T) dmw[k] = 0;
+        if (tid < 16) rcw[tid] = 0;
         if (tid < 4) ctrl[C_GDONE + tid] = 0;
         if (tid == 0) {
             ctrl[C_CLAIM] = 0;
             ctrl[C_ERR] = 0xFFFFFFFFu;
             ctrl[C_NVAL] = 0;
         }
+        D2_STAMP(1);
         d2_mbar_wait(bar, phase);
         phase ^= 1u;
         __syncthreads();
+        D2_STAMP(2);
         if (rle) { /* expand the literal stream to where raw literals would have been staged */
             if (wic == 0) {
-                const int rc = rle_expand(win + rle_at + g_lit_shift, lit_comp, win + lit_pos, n_lit, lane);
+                const u32 rp = rle_at + g_lit_shift;
+                const int rc = d2_rle_inplace(win, rp, rp + lit_comp, (u32)lit_pos, (u32)lit_pos + n_lit, lane);
                 if (lane == 0) ctrl[C_NVAL] = (u32)rc;
             }
             __syncthreads();
             const int rc = (int)vctrl[C_NVAL];
             __syncthreads();
             if (rc != ZXC_OK) {
-                if (tid == 0) P.status[j] = rc;
+                if (tid == 0) {
+                    if (rc == 1) { /* in-place expansion not possible for this stream: general kernel */
+                        P.status[j] = D2_DEFER;
+                        const u32 slot = atomicAdd(P.defer_count, 1u);
+                        if (slot < P.defer_cap) P.defer_list[slot] = j;
+                    } else {
+                        P.status[j] = rc;
+                    }
+                }
                 continue;
             }
         }
@@ -399,6 +482,7 @@ __global__ void __launch_bounds__(256, 2) zxc_decode2_kernel(const Decode2Params
             __syncthreads();
         }
 
+        D2_STAMP(3);
         /* ---- phase 1b: sequences -> records ---- */
         u32 carryE = 0, carryL = 0, carryO = 0;
         for (u32 base = 0; base < n_seq; base += T * D2_CHUNK) {
@@ -505,10 +589,10 @@ __global__ void __launch_bounds__(256, 2) zxc_decode2_kernel(const Decode2Params
         }
         __syncthreads();
 
+        D2_STAMP(4);
         /* ---- phase 2: output words ---- */
         D2Block B;
         B.win = win;
-        B.dm = dmw;
         B.rs = recs;
         B.rg = recg;
         B.dict = P.dict;
@@ -522,28 +606,46 @@ __global__ void __launch_bounds__(256, 2) zxc_decode2_kernel(const Decode2Params
         const u32 total16 = total & ~15u;
         const u32 le_mask = (2u << lane) - 1u;
 
+        const u32 n_rows = (total + 127u) / 128u;
+        D2Prog Pg;
+        Pg.lead = 0;
+        /* rows [0, Pg.lead) complete: extend the prefix over the row bitmap (acquire loads) */
+        auto refresh_lead = [&]() {
+            while (Pg.lead < n_rows) {
+                const u32 sh = Pg.lead & 31u;
+                const u32 m = d2_ld_acquire(rcw + (Pg.lead >> 5)) >> sh;
+                const u32 ones = (~m) ? (u32)(__ffs(~m) - 1) : 32u; /* zeros were shifted in above bit 31 - sh */
+                Pg.lead += ones;
+                if (ones == 0u || (Pg.lead & 31u) != 0u) break;
+            }
+        };
+        /* nothing to do until row Pg.lead completes: sleep on its barrier instead of polling */
+        auto sleep_on_lead = [&]() { d2_mbar_wait(rowbar + 8u * Pg.lead, row_par); };
+
+        unsigned long long tw_guard = 0, tw_plan = 0, tw_round = 0, tw_sleep = 0, tw_fin = 0, n_round = 0, n_sleep = 0, n_step = 0;
+        const bool tr = P.trace != NULL && wic == 0;
+#define D2_T() (tr ? (unsigned long long)clock64() : 0ull)
         for (;;) {
             u32 g = 0;
             if (lane == 0) g = atomicAdd(&ctrl[C_CLAIM], 1u);
             g = __shfl_sync(FULL, g, 0);
             if (g >= n_groups) break;
+            const unsigned long long tt0 = D2_T();
+            n_step++;
             /* staged literals above are overwritten by this group's output: every group that may
              * still read them (<= g - KGUARD) must be complete */
             if (g >= KGUARD) {
-                const u32 need = g - KGUARD + 1;
-                for (;;) {
-                    u32 lead = 0;
-#pragma unroll
-                    for (u32 w = 0; w < 4; w++) {
-                        const u32 m = vctrl[C_GDONE + w];
-                        if (lead == 32u * w) lead += (m == FULL) ? 32u : (u32)(__ffs(~m) - 1);
-                    }
-                    if (lead >= need) break;
-                    __nanosleep(40);
+                const u32 need = min(n_rows, Z2_ROWS * (g - KGUARD + 1));
+                while (Pg.lead < need) {
+                    refresh_lead();
+                    if (Pg.lead < need) sleep_on_lead();
                 }
             }
+            const unsigned long long tt1 = D2_T();
+            tw_guard += tt1 - tt0;
             const i32 p0 = (i32)(g * Z2_GROUP);
             const u32 i0 = gidx[g];
+            Pg.g4 = g * Z2_ROWS;
             /* sequence ends inside the group -> bitmask of the words where the next sequence starts */
             u32 M0 = 0, M1 = 0, M2 = 0, M3 = 0;
 #pragma unroll 1
@@ -568,7 +670,7 @@ __global__ void __launch_bounds__(256, 2) zxc_decode2_kernel(const Decode2Params
 
             i32 sX[Z2_ROWS], sY[Z2_ROWS], sZ[Z2_ROWS];
             u32 meta[Z2_ROWS]; /* t | t2 << 4 | flags << 8 | idx << 16 */
-            u32 pend = 0, dmask[Z2_ROWS];
+            u32 pend = 0, published = 0;
 #pragma unroll
             for (u32 r = 0; r < Z2_ROWS; r++) {
                 const u32 Mr = r == 0 ? M0 : r == 1 ? M1 : r == 2 ? M2 : M3;
@@ -584,23 +686,26 @@ __global__ void __launch_bounds__(256, 2) zxc_decode2_kernel(const Decode2Params
                 sZ[r] = pl.srcZ;
                 meta[r] = pl.t | (pl.t2 << 4) | (pl.flags << 8) | (idx << 16);
                 if (active) pend |= 1u << r;
-                dmask[r] = __ballot_sync(FULL, !active);
+                Pg.own[r] = __ballot_sync(FULL, !active);
             }
-            /* rounds: a word is gathered once its source words are complete */
+            refresh_lead();
+            unsigned long long tt2 = D2_T();
+            tw_plan += tt2 - tt1;
+            /* rounds: a word is gathered once the words it reads are complete */
             for (;;) {
+                n_round++;
                 u32 rdy = 0;
 #pragma unroll
                 for (u32 r = 0; r < Z2_ROWS; r++) {
                     const u32 fl = (meta[r] >> 8) & 0xFFu;
                     if (((pend >> r) & 1u) && !(fl & Z2_SLOW)) {
                         bool ok = true;
-                        if (fl & 1u) ok = d2_ready(B.dm, sX[r]);
-                        if ((fl & 2u) && ok) ok = d2_ready(B.dm, sY[r]);
-                        if ((fl & 4u) && ok) ok = d2_ready(B.dm, sZ[r]);
+                        if (fl & 1u) ok = d2_ready(Pg, sX[r]);
+                        if ((fl & 2u) && ok) ok = d2_ready(Pg, sY[r]);
+                        if ((fl & 4u) && ok) ok = d2_ready(Pg, sZ[r]);
                         if (ok) rdy |= 1u << r;
                     }
                 }
-                __threadfence_block(); /* acquire: the gathers below must see what the masks promised */
                 u32 did = 0;
 #pragma unroll
                 for (u32 r = 0; r < Z2_ROWS; r++) {
@@ -620,7 +725,7 @@ __global__ void __launch_bounds__(256, 2) zxc_decode2_kernel(const Decode2Params
                         did |= 1u << r;
                     } else if (((pend >> r) & 1u) && ((meta[r] >> 8) & Z2_SLOW)) {
                         u32 v;
-                        if (d2_slow_word(B, meta[r] >> 16, p, v)) {
+                        if (d2_slow_word(B, Pg, meta[r] >> 16, p, v)) {
                             *reinterpret_cast<volatile u32*>(win + p) = v;
                             did |= 1u << r;
                         }
@@ -628,33 +733,55 @@ __global__ void __launch_bounds__(256, 2) zxc_decode2_kernel(const Decode2Params
                 }
                 pend &= ~did;
                 bool progress = false;
+                u32 full = 0;
 #pragma unroll
                 for (u32 r = 0; r < Z2_ROWS; r++) {
                     const u32 m = __ballot_sync(FULL, (did >> r) & 1u);
-                    dmask[r] |= m;
+                    Pg.own[r] |= m;
                     progress |= m != 0u;
+                    if (Pg.own[r] == FULL) full |= 1u << r;
                 }
-                __threadfence_block(); /* release: words before masks */
-                __syncwarp();
-                if (lane < Z2_ROWS) {
-                    const u32 mine = lane == 0 ? dmask[0] : lane == 1 ? dmask[1] : lane == 2 ? dmask[2] : dmask[3];
-                    B.dm[g * Z2_ROWS + lane] = mine;
+                __syncwarp(); /* the words of this round are visible to the whole warp (next round reads them) */
+                const u32 fresh = full & ~published;
+                if (fresh) { /* rows that just completed: bitmap (release), then wake the sleepers */
+                    if (lane == 0) {
+                        d2_release_fence();
+                        atomicOr(rcw + (Pg.g4 >> 5), fresh << (Pg.g4 & 31u));
+#pragma unroll
+                        for (u32 r = 0; r < Z2_ROWS; r++)
+                            if ((fresh >> r) & 1u) d2_mbar_arrive(rowbar + 8u * (Pg.g4 + r));
+                    }
+                    published |= fresh;
                 }
                 if (!__any_sync(FULL, pend != 0u)) break;
-                if (!progress) __nanosleep(20);
+                if (!progress) {
+                    const u32 before = Pg.lead;
+                    refresh_lead();
+                    const unsigned long long ts0 = D2_T();
+                    if (Pg.lead == before && Pg.lead < Pg.g4) {
+                        sleep_on_lead();
+                        n_sleep++;
+                    }
+                    refresh_lead();
+                    const unsigned long long ts1 = D2_T();
+                    tw_sleep += ts1 - ts0;
+                    tt2 += ts1 - ts0;
+                }
             }
-            /* group complete: publish, and ship the 8 KiB chunk it may have completed */
+            const unsigned long long tt3 = D2_T();
+            tw_round += tt3 - tt2;
+            /* group complete: ship the 8 KiB chunk it may have completed */
             d2_fence_async();
             __syncwarp();
             if (lane == 0) {
-                __threadfence_block();
+                d2_release_fence();
                 const u32 wi = g >> 5, bit = 1u << (g & 31u);
                 const u32 old = atomicOr(&ctrl[C_GDONE + wi], bit);
                 if (bulk_ok) {
                     const u32 ch = g >> 4; /* 16 groups per chunk */
                     const u32 first = ch << 4;
                     const u32 cnt = min(16u, n_groups - first);
-                    const u32 cm = ((cnt >= 32u ? 0u : (1u << cnt)) - 1u) << (first & 31u);
+                    const u32 cm = ((1u << cnt) - 1u) << (first & 31u);
                     if (((old | bit) & cm) == cm) {
                         const u32 b0 = first * Z2_GROUP;
                         const u32 b1 = min(b0 + 16u * Z2_GROUP, total16);
@@ -665,16 +792,26 @@ __global__ void __launch_bounds__(256, 2) zxc_decode2_kernel(const Decode2Params
                     }
                 }
             }
+            tw_fin += D2_T() - tt3;
+        }
+        if (tr && lane == 0) { /* second half of the job's trace slots is not used by the phase stamps: reuse slot 7 and a side table */
+            unsigned long long* q = P.trace + (size_t)P.n_jobs * 8 + (size_t)j * 8;
+            q[0] = tw_guard; q[1] = tw_plan; q[2] = tw_round; q[3] = tw_sleep; q[4] = tw_fin; q[5] = n_round; q[6] = n_sleep; q[7] = n_step;
         }
         __syncthreads();
+        D2_STAMP(5);
         if (bulk_ok) {
             for (u32 k = total16 + tid; k < total; k += T) out[k] = win[k];
         } else {
             for (u32 k = tid; k < total; k += T) out[k] = win[k];
         }
+        /* every row barrier advances exactly one phase per decoded block: the rows this block did not have */
+        for (u32 r = n_groups * Z2_ROWS + tid; r < rows_max; r += T) d2_mbar_arrive(rowbar + 8u * r);
+        row_par ^= 1u;
         if (tid == 0) P.status[j] = result;
         d2_bulk_wait_read();
         __syncthreads();
+        D2_STAMP(6);
     }
     d2_bulk_wait_all();
 }

@@ -36,52 +36,234 @@ static pthread_mutex_t g_pool_mu = PTHREAD_MUTEX_INITIALIZER;
 
 #define PIN_CHUNK ((size_t)32 << 20)
 
-/* Pageable host buffers are staged through pinned bounce buffers; one thread's memcpy (~10 GB/s)
- * would be far below PCIe Gen5, so large copies are split over a few helper threads. */
-#define STAGE_THREADS 6
-struct stage_job { void* d; const void* s; size_t n; };
-static void* stage_worker(void* p) {
-    const stage_job* j = (const stage_job*)p;
-    memcpy(j->d, j->s, j->n);
+/* ------------------------------------------------------------------------- */
+/* Host copy pool.  Pageable caller buffers are staged through pinned bounce  */
+/* buffers; one thread's memcpy (~10 GB/s) is far below a PCIe Gen5 link, so   */
+/* copies are cut into slices that a few persistent threads claim.  There is   */
+/* one pool per device, created on first use, its threads bound to the CPUs of  */
+/* the device's NUMA node (/sys/bus/pci/devices/<bdf>/numa_node), which is also */
+/* where the bounce buffers are placed: on the 8-GPU hosts GPUs 0-3 hang off    */
+/* node 0 and 4-7 off node 1, and unplaced staging memory made the 8-rank       */
+/* host-to-host figure of round 1 fall below the 4-rank one.                    */
+/* ------------------------------------------------------------------------- */
+#include <sched.h>
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
+#define POOL_MAX_DEV 16
+#define POOL_MAX_THREADS 16
+#define POOL_SLICE ((size_t)512 << 10)
+
+struct copy_pool {
+    pthread_mutex_t job_mu; /* one job at a time */
+    pthread_mutex_t mu;
+    pthread_cond_t cv_go, cv_done;
+    pthread_t th[POOL_MAX_THREADS];
+    int n_threads, started;
+    int numa_node; /* -1 unknown */
+    cpu_set_t cpus;
+    int have_cpus;
+    /* current job */
+    u8* d;
+    const u8* s;
+    size_t bytes;
+    size_t next; /* next slice offset (atomic) */
+    unsigned long gen;
+    int busy;    /* workers still inside the current job */
+};
+static copy_pool g_pools[POOL_MAX_DEV];
+static pthread_mutex_t g_pools_mu = PTHREAD_MUTEX_INITIALIZER;
+
+static int device_numa_node(int dev) {
+    char bdf[32];
+    if (cudaDeviceGetPCIBusId(bdf, sizeof bdf, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    for (char* p = bdf; *p; p++)
+        if (*p >= 'A' && *p <= 'F') *p = (char)(*p - 'A' + 'a');
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bdf);
+    FILE* f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+}
+
+static int node_cpu_set(int node, cpu_set_t* set) {
+    char path[128];
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    FILE* f = fopen(path, "r");
+    if (!f) return 0;
+    CPU_ZERO(set);
+    int a, b, any = 0;
+    for (;;) {
+        if (fscanf(f, "%d", &a) != 1) break;
+        b = a;
+        int ch = fgetc(f);
+        if (ch == '-') {
+            if (fscanf(f, "%d", &b) != 1) break;
+            ch = fgetc(f);
+        }
+        for (int c = a; c <= b && c < CPU_SETSIZE; c++) {
+            CPU_SET(c, set);
+            any = 1;
+        }
+        if (ch != ',') break;
+    }
+    fclose(f);
+    /* stay inside what the process may use */
+    cpu_set_t allowed;
+    if (any && sched_getaffinity(0, sizeof allowed, &allowed) == 0) {
+        CPU_AND(set, set, &allowed);
+        any = CPU_COUNT(set) > 0;
+    }
+    return any;
+}
+
+static void pool_run_slices(copy_pool* p) {
+    for (;;) {
+        const size_t off = __atomic_fetch_add(&p->next, POOL_SLICE, __ATOMIC_RELAXED);
+        if (off >= p->bytes) break;
+        const size_t n = p->bytes - off < POOL_SLICE ? p->bytes - off : POOL_SLICE;
+        memcpy(p->d + off, p->s + off, n);
+    }
+}
+
+static void* pool_worker(void* arg) {
+    copy_pool* p = (copy_pool*)arg;
+    if (p->have_cpus) pthread_setaffinity_np(pthread_self(), sizeof p->cpus, &p->cpus);
+    unsigned long seen = 0;
+    pthread_mutex_lock(&p->mu);
+    for (;;) {
+        while (p->gen == seen) pthread_cond_wait(&p->cv_go, &p->mu);
+        seen = p->gen;
+        pthread_mutex_unlock(&p->mu);
+        pool_run_slices(p);
+        pthread_mutex_lock(&p->mu);
+        if (--p->busy == 0) pthread_cond_signal(&p->cv_done);
+    }
     return NULL;
 }
-static void parallel_memcpy(void* dst, const void* src, size_t n) {
-    if (n < ((size_t)4 << 20)) {
+
+static copy_pool* pool_for_device(int dev) {
+    if (dev < 0 || dev >= POOL_MAX_DEV) dev = 0;
+    copy_pool* p = &g_pools[dev];
+    if (__atomic_load_n(&p->started, __ATOMIC_ACQUIRE)) return p;
+    pthread_mutex_lock(&g_pools_mu);
+    if (!p->started) {
+        pthread_mutex_init(&p->job_mu, NULL);
+        pthread_mutex_init(&p->mu, NULL);
+        pthread_cond_init(&p->cv_go, NULL);
+        pthread_cond_init(&p->cv_done, NULL);
+        p->numa_node = device_numa_node(dev);
+        p->have_cpus = p->numa_node >= 0 && node_cpu_set(p->numa_node, &p->cpus);
+        long ncpu = p->have_cpus ? CPU_COUNT(&p->cpus) : sysconf(_SC_NPROCESSORS_ONLN);
+        const char* e = getenv("ZXC_B200_COPY_THREADS");
+        int want = e ? atoi(e) : (int)(ncpu / 4);
+        if (want < 2) want = 2;
+        if (want > POOL_MAX_THREADS) want = POOL_MAX_THREADS;
+        p->n_threads = 0;
+        for (int t = 0; t < want - 1; t++) /* the caller is the last member of every job */
+            if (pthread_create(&p->th[p->n_threads], NULL, pool_worker, p) == 0) p->n_threads++;
+        __atomic_store_n(&p->started, 1, __ATOMIC_RELEASE);
+    }
+    pthread_mutex_unlock(&g_pools_mu);
+    return p;
+}
+
+static void pool_memcpy(int dev, void* dst, const void* src, size_t n) {
+    if (n < ((size_t)2 << 20)) {
         memcpy(dst, src, n);
         return;
     }
-    pthread_t th[STAGE_THREADS];
-    stage_job jobs[STAGE_THREADS];
-    const size_t per = ((n / STAGE_THREADS) + 4095) & ~(size_t)4095;
-    int started = 0;
-    size_t off = 0;
-    for (int t = 0; t < STAGE_THREADS && off < n; t++) {
-        const size_t len = (t == STAGE_THREADS - 1 || off + per > n) ? n - off : per;
-        jobs[t].d = (u8*)dst + off;
-        jobs[t].s = (const u8*)src + off;
-        jobs[t].n = len;
-        off += len;
-        if (t == 0) continue; /* the calling thread takes the first slice */
-        if (pthread_create(&th[started], NULL, stage_worker, &jobs[t]) != 0) {
-            memcpy(jobs[t].d, jobs[t].s, jobs[t].n);
-            continue;
-        }
-        started++;
-    }
-    memcpy(jobs[0].d, jobs[0].s, jobs[0].n);
-    for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
+    copy_pool* p = pool_for_device(dev);
+    pthread_mutex_lock(&p->job_mu);
+    pthread_mutex_lock(&p->mu);
+    p->d = (u8*)dst;
+    p->s = (const u8*)src;
+    p->bytes = n;
+    p->next = 0;
+    p->busy = p->n_threads;
+    p->gen++;
+    pthread_cond_broadcast(&p->cv_go);
+    pthread_mutex_unlock(&p->mu);
+    pool_run_slices(p);
+    pthread_mutex_lock(&p->mu);
+    while (p->busy) pthread_cond_wait(&p->cv_done, &p->mu);
+    pthread_mutex_unlock(&p->mu);
+    pthread_mutex_unlock(&p->job_mu);
 }
+
+/* page-locked memory on the device's NUMA node: anonymous mapping, preferred-node policy, touched,
+ * then registered with CUDA.  Falls back to cudaMallocHost when the node is unknown. */
+struct pinned_buf {
+    void* p;
+    size_t bytes;
+    int mapped; /* 1: mmap + cudaHostRegister, 0: cudaMallocHost */
+};
+static int pinned_alloc(pinned_buf* b, size_t bytes, int node) {
+    b->p = NULL;
+    b->bytes = bytes;
+    b->mapped = 0;
+    if (node >= 0 && node < 64) {
+        void* m = mmap(NULL, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (m != MAP_FAILED) {
+            unsigned long mask = 1ul << node;
+#ifdef SYS_mbind
+            syscall(SYS_mbind, m, bytes, 1 /* MPOL_PREFERRED */, &mask, sizeof(mask) * 8, 0);
+#endif
+            memset(m, 0, bytes);
+            if (cudaHostRegister(m, bytes, cudaHostRegisterDefault) == cudaSuccess) {
+                b->p = m;
+                b->mapped = 1;
+                return ZXC_OK;
+            }
+            cudaGetLastError();
+            munmap(m, bytes);
+        }
+    }
+    if (cudaMallocHost(&b->p, bytes) != cudaSuccess) {
+        b->p = NULL;
+        return ZXC_ERROR_MEMORY;
+    }
+    return ZXC_OK;
+}
+static void pinned_free(pinned_buf* b) {
+    if (!b->p) return;
+    if (b->mapped) {
+        cudaHostUnregister(b->p);
+        munmap(b->p, b->bytes);
+    } else {
+        cudaFreeHost(b->p);
+    }
+    b->p = NULL;
+}
+
+#define STAGE_SLOTS 3
+#define EV_RING 8
 
 struct zxg_ctx {
     cudaStream_t stream;
     void* buf[ZXG_BUF_COUNT];
     size_t cap[ZXG_BUF_COUNT];
+    pinned_buf pinb[2];
     void* pin[2];
     cudaEvent_t pin_ev[2];
-    unsigned long long* counter; /* [0] work counter, [1..2] reduce output */
-    cudaStream_t s_h2d, s_d2h;   /* copy engines for the pipelined frame path (lazily created) */
+    unsigned long long* counter; /* [0..1] work counters, [2] deferred-job counter */
+    unsigned long long* reduce_out; /* device: [0] first bad index, [1] byte sum (zxc_b200_reduce_status) */
+    cudaStream_t s_h2d, s_d2h;   /* copy engines for the pipelined frame paths (lazily created) */
+    cudaEvent_t ev_ring[EV_RING]; /* reused by the pipelines: no event is created per chunk */
+    pinned_buf st_in[STAGE_SLOTS], st_out[STAGE_SLOTS]; /* staging for pageable callers (lazily allocated) */
+    cudaEvent_t st_ev_in[STAGE_SLOTS], st_ev_dec[STAGE_SLOTS], st_ev_out[STAGE_SLOTS];
+    int st_ready;
     struct zxg_ctx* next;
     int device;
+    int numa_node;
+    int sm_count;
 };
 static zxg_ctx* g_free_list = NULL;
 
@@ -126,10 +308,15 @@ extern "C" zxg_ctx* zxg_create(void) {
     if (!c) return NULL;
     cudaGetDevice(&c->device);
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc((void**)&c->counter, 4 * sizeof(unsigned long long)) != cudaSuccess) {
+        cudaMalloc((void**)&c->counter, 8 * sizeof(unsigned long long)) != cudaSuccess) {
         free(c);
         return NULL;
     }
+    c->reduce_out = c->counter + 4;
+    c->numa_node = device_numa_node(c->device);
+    int smc = 0;
+    if (cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, c->device) != cudaSuccess || smc <= 0) smc = g_sm_count;
+    c->sm_count = smc;
     return c;
 }
 
@@ -139,9 +326,18 @@ extern "C" void zxg_destroy(zxg_ctx* c) {
     for (int i = 0; i < ZXG_BUF_COUNT; i++)
         if (c->buf[i]) cudaFree(c->buf[i]);
     for (int i = 0; i < 2; i++) {
-        if (c->pin[i]) cudaFreeHost(c->pin[i]);
+        pinned_free(&c->pinb[i]);
         if (c->pin_ev[i]) cudaEventDestroy(c->pin_ev[i]);
     }
+    for (int i = 0; i < STAGE_SLOTS; i++) {
+        pinned_free(&c->st_in[i]);
+        pinned_free(&c->st_out[i]);
+        if (c->st_ev_in[i]) cudaEventDestroy(c->st_ev_in[i]);
+        if (c->st_ev_dec[i]) cudaEventDestroy(c->st_ev_dec[i]);
+        if (c->st_ev_out[i]) cudaEventDestroy(c->st_ev_out[i]);
+    }
+    for (int i = 0; i < EV_RING; i++)
+        if (c->ev_ring[i]) cudaEventDestroy(c->ev_ring[i]);
     cudaFree(c->counter);
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
@@ -212,7 +408,8 @@ static int host_is_pinned(const void* p) {
 static int ensure_pins(zxg_ctx* c) {
     for (int i = 0; i < 2; i++) {
         if (!c->pin[i]) {
-            if (cudaMallocHost(&c->pin[i], PIN_CHUNK) != cudaSuccess) return ZXC_ERROR_MEMORY;
+            if (pinned_alloc(&c->pinb[i], PIN_CHUNK, c->numa_node) != ZXC_OK) return ZXC_ERROR_MEMORY;
+            c->pin[i] = c->pinb[i].p;
             if (cudaEventCreateWithFlags(&c->pin_ev[i], cudaEventDisableTiming) != cudaSuccess)
                 return ZXC_B200_ERROR_CUDA;
         }
@@ -233,7 +430,7 @@ extern "C" int zxg_h2d(zxg_ctx* c, void* d_dst, const void* h_src, size_t bytes)
     while (done < bytes) {
         const size_t n = bytes - done < PIN_CHUNK ? bytes - done : PIN_CHUNK;
         cudaEventSynchronize(c->pin_ev[slot]); /* previous use of this bounce buffer */
-        parallel_memcpy(c->pin[slot], (const u8*)h_src + done, n);
+        pool_memcpy(c->device, c->pin[slot], (const u8*)h_src + done, n);
         if (cudaMemcpyAsync((u8*)d_dst + done, c->pin[slot], n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
             return ZXC_B200_ERROR_CUDA;
         cudaEventRecord(c->pin_ev[slot], c->stream);
@@ -266,7 +463,7 @@ extern "C" int zxg_d2h(zxg_ctx* c, void* h_dst, const void* d_src, size_t bytes)
             const size_t off = (k - 1) * PIN_CHUNK;
             const size_t n = bytes - off < PIN_CHUNK ? bytes - off : PIN_CHUNK;
             if (cudaEventSynchronize(c->pin_ev[(k - 1) & 1]) != cudaSuccess) return ZXC_B200_ERROR_CUDA;
-            parallel_memcpy((u8*)h_dst + off, c->pin[(k - 1) & 1], n);
+            pool_memcpy(c->device, (u8*)h_dst + off, c->pin[(k - 1) & 1], n);
         }
     }
     return ZXC_OK;
@@ -301,7 +498,7 @@ static int d2_enabled(void) {
     static int cached = -1;
     if (cached < 0) {
         const char* e = getenv("ZXC_B200_DECODE_V2");
-        cached = (e && e[0] == '0') ? 0 : 1;
+        cached = (e && e[0] == '1') ? 1 : 0; /* off: measured slower than the warp-per-block kernel */
     }
     return cached;
 }
@@ -367,6 +564,17 @@ static int launch_decode(const void* d_src, void* d_dst, const zxc_b200_job_t* d
     P.dict_size = d_dict ? dict_size : 0;
     P.scratch_stride = scratch_stride_for(block_size);
     P.flags = verify ? FLAG_VERIFY : 0;
+    {
+        static int units_mode = -2; /* ZXC_B200_UNITS: 1 = always, 0 = never, unset = by measured rule */
+        if (units_mode == -2) {
+            const char* e = getenv("ZXC_B200_UNITS");
+            units_mode = e ? (e[0] == '1' ? 1 : 0) : -1;
+        }
+        if (units_mode == 1) P.flags |= FLAG_UNITS_ON;
+        if (units_mode == 0) P.flags |= FLAG_UNITS_OFF;
+    }
+    /* the output-centric body where it measured faster: dictionary decodes of small blocks */
+    const bool units = (P.flags & FLAG_UNITS_ON) || (!(P.flags & FLAG_UNITS_OFF) && P.dict_size != 0 && block_size <= 16384u);
     P.block_cap = block_size;
     P.defer_list = NULL;
     P.defer_count = NULL;
@@ -414,13 +622,48 @@ static int launch_decode(const void* d_src, void* d_dst, const zxc_b200_job_t* d
         P.defer_list = Q.defer_list;
         P.defer_count = Q.defer_count;
         P.defer_cap = Q.defer_cap;
+        Q.trace = NULL;
+        const int want_trace = getenv("ZXC_B200_D2_TRACE") != NULL; /* development: per-phase cycle counts */
+        if (want_trace && cudaMalloc((void**)&Q.trace, (size_t)n_jobs * 128) == cudaSuccess)
+            cudaMemsetAsync(Q.trace, 0, (size_t)n_jobs * 128, st);
         zxc_decode2_kernel<<<grid2, c.threads, c.smem, st>>>(Q);
         __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
         if (cudaGetLastError() != cudaSuccess) return ZXC_B200_ERROR_CUDA;
+        if (Q.trace) {
+            unsigned long long* h = (unsigned long long*)malloc((size_t)n_jobs * 128);
+            cudaStreamSynchronize(st);
+            cudaMemcpy(h, Q.trace, (size_t)n_jobs * 128, cudaMemcpyDeviceToHost);
+            double acc[6] = {0, 0, 0, 0, 0, 0};
+            u32 cnt = 0;
+            for (u32 i = 0; i < n_jobs; i++) {
+                const unsigned long long* t = h + (size_t)i * 8;
+                if (!t[6] || !t[5]) continue; /* deferred / raw / failed jobs leave the later stamps empty */
+                for (int q = 0; q < 6; q++) acc[q] += (double)(t[q + 1] - t[q]);
+                cnt++;
+            }
+            if (cnt)
+                fprintf(stderr, "d2 trace (%u blocks, mean cycles): header+issue %.0f | load wait %.0f | extras %.0f | records %.0f | "
+                                "words %.0f | drain %.0f\n", cnt, acc[0] / cnt, acc[1] / cnt, acc[2] / cnt, acc[3] / cnt,
+                        acc[4] / cnt, acc[5] / cnt);
+            double w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (u32 i = 0; i < n_jobs; i++) {
+                const unsigned long long* t = h + (size_t)i * 8;
+                if (!t[6] || !t[5]) continue;
+                for (int q = 0; q < 8; q++) w[q] += (double)h[(size_t)n_jobs * 8 + (size_t)i * 8 + q];
+            }
+            if (cnt)
+                fprintf(stderr, "d2 trace warp 0 per block: steps %.1f rounds %.1f sleeps %.1f | cycles: guard %.0f plan %.0f rounds %.0f "
+                                "sleep %.0f finish %.0f\n", w[7] / cnt, w[5] / cnt, w[6] / cnt, w[0] / cnt, w[1] / cnt, w[2] / cnt,
+                        w[3] / cnt, w[4] / cnt);
+            free(h);
+            cudaFree(Q.trace);
+        }
         P.flags |= FLAG_DEFERRED;
         P.counter = d_counter + 1;
     }
-    zxc_decode_kernel<<<grid, CTA_THREADS, DECODE_SMEM_BYTES, st>>>(P);
+    if (P.flags & FLAG_DEFERRED) zxc_decode_kernel<false, true><<<grid, CTA_THREADS, DECODE_SMEM_BYTES, st>>>(P);
+    else if (units) zxc_decode_kernel<true, false><<<grid, CTA_THREADS, DECODE_SMEM_BYTES, st>>>(P);
+    else zxc_decode_kernel<false, false><<<grid, CTA_THREADS, DECODE_SMEM_BYTES, st>>>(P);
     __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
     return cudaGetLastError() == cudaSuccess ? ZXC_OK : ZXC_B200_ERROR_CUDA;
 }
@@ -453,14 +696,26 @@ extern "C" int zxc_b200_decode_blocks(const void* d_src, void* d_dst, const zxc_
                          d_scratch, usable, block_size, verify_checksums, counter, (cudaStream_t)stream);
 }
 
+/* one 16-byte result slot per device, allocated on first use and kept: no cudaMalloc / cudaFree per call */
+static unsigned long long* g_reduce_dev[POOL_MAX_DEV];
+static pthread_mutex_t g_reduce_mu = PTHREAD_MUTEX_INITIALIZER;
+
 extern "C" int64_t zxc_b200_reduce_status(const int32_t* d_status, const zxc_b200_job_t* d_jobs,
                                           uint32_t n_jobs, void* stream) {
     const int rc = zxg_init();
     if (rc != ZXC_OK) return rc;
     if (n_jobs == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    unsigned long long* d_out = NULL;
-    if (cudaMalloc((void**)&d_out, 16) != cudaSuccess) return ZXC_ERROR_MEMORY;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= POOL_MAX_DEV) dev = 0;
+    pthread_mutex_lock(&g_reduce_mu);
+    if (!g_reduce_dev[dev] && cudaMalloc((void**)&g_reduce_dev[dev], 16) != cudaSuccess) {
+        g_reduce_dev[dev] = NULL;
+        pthread_mutex_unlock(&g_reduce_mu);
+        return ZXC_ERROR_MEMORY;
+    }
+    unsigned long long* d_out = g_reduce_dev[dev];
     const unsigned long long init[2] = {~0ull, 0ull};
     cudaMemcpyAsync(d_out, init, 16, cudaMemcpyHostToDevice, st);
     zxc_reduce_kernel<<<(n_jobs + 255) / 256, 256, 0, st>>>(d_status, d_jobs, n_jobs, d_out);
@@ -478,7 +733,7 @@ extern "C" int64_t zxc_b200_reduce_status(const int32_t* d_status, const zxc_b20
     } else {
         ret = (int64_t)h[1];
     }
-    cudaFree(d_out);
+    pthread_mutex_unlock(&g_reduce_mu);
     return ret;
 }
 
@@ -556,20 +811,20 @@ extern "C" int zxg_decode_pipelined(zxg_ctx* c, const uint8_t* h_src, uint64_t s
         return ZXC_B200_ERROR_CUDA;
 
     const uint64_t chunk_target = (uint64_t)64 << 20; /* decoded bytes per pipeline stage */
-    cudaEvent_t ev_in, ev_dec;
+    for (int i = 0; i < EV_RING; i++)
+        if (!c->ev_ring[i] && cudaEventCreateWithFlags(&c->ev_ring[i], cudaEventDisableTiming) != cudaSuccess)
+            return ZXC_B200_ERROR_CUDA;
     int rc = ZXC_OK;
-    uint32_t j0 = 0;
+    uint32_t j0 = 0, chunk_no = 0;
     while (j0 < n_jobs && rc == ZXC_OK) {
+        /* events are recycled: a wait refers to the record that preceded it, so reuse is safe */
+        const cudaEvent_t ev_in = c->ev_ring[(2u * chunk_no) % EV_RING], ev_dec = c->ev_ring[(2u * chunk_no + 1u) % EV_RING];
+        chunk_no++;
         uint32_t j1 = j0;
         uint64_t acc = 0;
         while (j1 < n_jobs && acc < chunk_target) acc += h_jobs[j1++].dst_cap;
         const uint64_t s0 = h_jobs[j0].src_off, s1 = h_jobs[j1 - 1].src_off + h_jobs[j1 - 1].src_len;
         const uint64_t o0 = h_jobs[j0].dst_off, o1 = h_jobs[j1 - 1].dst_off + h_jobs[j1 - 1].dst_cap;
-        if (cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ev_dec, cudaEventDisableTiming) != cudaSuccess) {
-            rc = ZXC_B200_ERROR_CUDA;
-            break;
-        }
         if (cudaMemcpyAsync(d_in + (s0 - src_lo), h_src + s0, (size_t)(s1 - s0), cudaMemcpyHostToDevice, c->s_h2d) != cudaSuccess)
             rc = ZXC_B200_ERROR_CUDA;
         cudaEventRecord(ev_in, c->s_h2d);
@@ -582,8 +837,6 @@ extern "C" int zxg_decode_pipelined(zxg_ctx* c, const uint8_t* h_src, uint64_t s
         if (rc == ZXC_OK &&
             cudaMemcpyAsync(h_dst + o0, d_out + o0, (size_t)(o1 - o0), cudaMemcpyDeviceToHost, c->s_d2h) != cudaSuccess)
             rc = ZXC_B200_ERROR_CUDA;
-        cudaEventDestroy(ev_in); /* deferred by the runtime until the events complete */
-        cudaEventDestroy(ev_dec);
         j0 = j1;
     }
     if (rc == ZXC_OK &&
@@ -599,6 +852,148 @@ extern "C" int zxg_decode_pipelined(zxg_ctx* c, const uint8_t* h_src, uint64_t s
     return rc;
 }
 
+
+/* ------------------------------------------------------------------------- */
+/* Staged frame decode for ordinary (pageable) caller memory: the same three     */
+/* streams as zxg_decode_pipelined, with pinned bounce buffers either side.  The  */
+/* host thread fills input slot k (copy pool, or the caller's read_at), queues    */
+/* H2D / decode / D2H for chunk k, then drains output slot k-2 into the caller's   */
+/* buffer while the GPU works -- so PCIe in, the SMs, PCIe out and the host copies */
+/* all overlap.  Decoded coordinates: job dst offsets; [clip_lo, clip_hi) of them  */
+/* is what the caller wants at h_dst (ranges start and end inside blocks).         */
+/* ------------------------------------------------------------------------- */
+#define STAGE_OUT ((size_t)32 << 20)
+#define STAGE_IN (STAGE_OUT + ((size_t)1 << 20))
+
+static int staged_ready(zxg_ctx* c) {
+    if (c->st_ready) return ZXC_OK;
+    for (int i = 0; i < STAGE_SLOTS; i++) {
+        if (!c->st_in[i].p && pinned_alloc(&c->st_in[i], STAGE_IN, c->numa_node) != ZXC_OK) return ZXC_ERROR_MEMORY;
+        if (!c->st_out[i].p && pinned_alloc(&c->st_out[i], STAGE_OUT, c->numa_node) != ZXC_OK) return ZXC_ERROR_MEMORY;
+        if (!c->st_ev_in[i] && cudaEventCreateWithFlags(&c->st_ev_in[i], cudaEventDisableTiming) != cudaSuccess) return ZXC_B200_ERROR_CUDA;
+        if (!c->st_ev_dec[i] && cudaEventCreateWithFlags(&c->st_ev_dec[i], cudaEventDisableTiming) != cudaSuccess) return ZXC_B200_ERROR_CUDA;
+        if (!c->st_ev_out[i] && cudaEventCreateWithFlags(&c->st_ev_out[i], cudaEventDisableTiming) != cudaSuccess) return ZXC_B200_ERROR_CUDA;
+    }
+    if (!c->s_h2d && cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking) != cudaSuccess) return ZXC_B200_ERROR_CUDA;
+    if (!c->s_d2h && cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking) != cudaSuccess) return ZXC_B200_ERROR_CUDA;
+    c->st_ready = 1;
+    return ZXC_OK;
+}
+
+struct staged_chunk {
+    uint32_t j0, j1;
+    uint64_t s0, s1;   /* source byte range */
+    uint64_t c0, c1;   /* clipped decoded range delivered to the caller */
+};
+
+extern "C" int zxg_decode_staged(zxg_ctx* c, const uint8_t* h_src, zxg_fetch_fn fetch, void* fetch_ctx, uint64_t src_lo,
+                                 uint64_t src_hi, uint8_t* h_dst, uint64_t clip_lo, uint64_t clip_hi,
+                                 const zxc_b200_job_t* h_jobs, uint32_t n_jobs, int32_t* h_status, const void* h_dict,
+                                 uint32_t dict_size, const void* h_dict_huf, uint32_t block_size, int verify_checksums) {
+    if (n_jobs == 0) return ZXC_OK;
+    int rc = staged_ready(c);
+    if (rc != ZXC_OK) return rc;
+    const uint64_t produced = h_jobs[n_jobs - 1].dst_off + h_jobs[n_jobs - 1].dst_cap;
+    u8* d_in = (u8*)zxg_buffer(c, ZXG_BUF_IN, (size_t)(src_hi - src_lo) + 16);
+    u8* d_out = (u8*)zxg_buffer(c, ZXG_BUF_OUT, (size_t)produced + 16);
+    zxc_b200_job_t* d_jobs = (zxc_b200_job_t*)zxg_buffer(c, ZXG_BUF_JOBS, (size_t)n_jobs * sizeof(zxc_b200_job_t));
+    i32* d_status = (i32*)zxg_buffer(c, ZXG_BUF_STATUS, (size_t)n_jobs * sizeof(i32));
+    const size_t scratch_size = launch_scratch_bytes(n_jobs, block_size);
+    void* d_scratch = zxg_buffer(c, ZXG_BUF_SCRATCH, scratch_size);
+    if (!d_in || !d_out || !d_jobs || !d_status || !d_scratch) return ZXC_ERROR_MEMORY;
+    u8* d_dict = NULL;
+    u8* d_huf = NULL;
+    if (h_dict && dict_size) {
+        d_dict = (u8*)zxg_buffer(c, ZXG_BUF_DICT, (size_t)dict_size + 128);
+        if (!d_dict) return ZXC_ERROR_MEMORY;
+        rc = zxg_h2d(c, d_dict, h_dict, dict_size);
+        if (rc == ZXC_OK && h_dict_huf) {
+            d_huf = d_dict + dict_size;
+            rc = zxg_h2d(c, d_huf, h_dict_huf, 128);
+        }
+        if (rc != ZXC_OK) return rc;
+    }
+    if (cudaMemcpyAsync(d_jobs, h_jobs, (size_t)n_jobs * sizeof(zxc_b200_job_t), cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+        return ZXC_B200_ERROR_CUDA;
+    cudaStreamSynchronize(c->stream); /* h_jobs may be pageable: do not let the caller free it under the copy */
+
+    staged_chunk ring[STAGE_SLOTS];
+    uint32_t j0 = 0, issued = 0, drained = 0;
+    while (rc == ZXC_OK && (drained < issued || j0 < n_jobs)) {
+        if (j0 < n_jobs && issued - drained < STAGE_SLOTS) { /* a slot is free: stage and queue the next chunk */
+            const int slot = (int)(issued % STAGE_SLOTS);
+            staged_chunk ch;
+            ch.j0 = j0;
+            uint32_t j1 = j0;
+            uint64_t acc_out = 0, acc_in = 0;
+            while (j1 < n_jobs && acc_out + h_jobs[j1].dst_cap <= STAGE_OUT && acc_in + h_jobs[j1].src_len <= STAGE_IN) {
+                acc_out += h_jobs[j1].dst_cap;
+                acc_in += h_jobs[j1].src_len;
+                j1++;
+            }
+            if (j1 == j0) { /* a single block larger than a stage: cannot happen with <= 2 MiB blocks */
+                rc = ZXC_ERROR_MEMORY;
+                break;
+            }
+            ch.j1 = j1;
+            ch.s0 = h_jobs[j0].src_off;
+            ch.s1 = h_jobs[j1 - 1].src_off + h_jobs[j1 - 1].src_len;
+            const uint64_t o0 = h_jobs[j0].dst_off, o1 = h_jobs[j1 - 1].dst_off + h_jobs[j1 - 1].dst_cap;
+            ch.c0 = o0 > clip_lo ? o0 : clip_lo;
+            ch.c1 = o1 < clip_hi ? o1 : clip_hi;
+            if (ch.c1 < ch.c0) ch.c1 = ch.c0;
+            cudaEventSynchronize(c->st_ev_in[slot]); /* the slot's previous H2D has left the bounce buffer */
+            u8* pin = (u8*)c->st_in[slot].p;
+            if (fetch) {
+                rc = fetch(fetch_ctx, pin, (size_t)(ch.s1 - ch.s0), ch.s0);
+                if (rc != ZXC_OK) break;
+            } else {
+                pool_memcpy(c->device, pin, h_src + ch.s0, (size_t)(ch.s1 - ch.s0));
+            }
+            if (cudaMemcpyAsync(d_in + (ch.s0 - src_lo), pin, (size_t)(ch.s1 - ch.s0), cudaMemcpyHostToDevice, c->s_h2d) != cudaSuccess) {
+                rc = ZXC_B200_ERROR_CUDA;
+                break;
+            }
+            cudaEventRecord(c->st_ev_in[slot], c->s_h2d);
+            cudaStreamWaitEvent(c->stream, c->st_ev_in[slot], 0);
+            rc = launch_decode(d_in - src_lo, d_out, d_jobs + j0, j1 - j0, d_status + j0, d_dict, dict_size, d_huf, d_scratch,
+                               scratch_size, block_size, verify_checksums, c->counter, c->stream);
+            if (rc != ZXC_OK) break;
+            cudaEventRecord(c->st_ev_dec[slot], c->stream);
+            cudaStreamWaitEvent(c->s_d2h, c->st_ev_dec[slot], 0);
+            if (ch.c1 > ch.c0 &&
+                cudaMemcpyAsync(c->st_out[slot].p, d_out + ch.c0, (size_t)(ch.c1 - ch.c0), cudaMemcpyDeviceToHost, c->s_d2h) != cudaSuccess) {
+                rc = ZXC_B200_ERROR_CUDA;
+                break;
+            }
+            cudaEventRecord(c->st_ev_out[slot], c->s_d2h);
+            ring[slot] = ch;
+            j0 = j1;
+            issued++;
+            if (j0 < n_jobs && issued - drained < STAGE_SLOTS) continue; /* fill the pipeline before draining */
+        }
+        /* hand the oldest finished chunk to the caller while the GPU works on the younger ones */
+        const int ds = (int)(drained % STAGE_SLOTS);
+        if (cudaEventSynchronize(c->st_ev_out[ds]) != cudaSuccess) {
+            rc = ZXC_B200_ERROR_CUDA;
+            break;
+        }
+        const staged_chunk& dc = ring[ds];
+        if (dc.c1 > dc.c0) pool_memcpy(c->device, h_dst + (dc.c0 - clip_lo), c->st_out[ds].p, (size_t)(dc.c1 - dc.c0));
+        drained++;
+    }
+    if (rc == ZXC_OK &&
+        cudaMemcpyAsync(h_status, d_status, (size_t)n_jobs * sizeof(i32), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+        rc = ZXC_B200_ERROR_CUDA;
+    const cudaError_t e1 = cudaStreamSynchronize(c->stream);
+    const cudaError_t e2 = cudaStreamSynchronize(c->s_d2h);
+    const cudaError_t e3 = cudaStreamSynchronize(c->s_h2d);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+        fprintf(stderr, "libzxc (B200 build): staged decode failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+        return ZXC_B200_ERROR_CUDA;
+    }
+    return rc;
+}
 
 /* ------------------------------------------------------------------------- */
 /* frame body encode: blocks -> per-block slots -> compacted body             */

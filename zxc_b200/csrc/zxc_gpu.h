@@ -62,6 +62,17 @@ int zxg_decode_pipelined(zxg_ctx* c, const uint8_t* h_src, uint64_t src_lo, uint
                          const void* h_dict, uint32_t dict_size, const void* h_dict_huf, uint32_t block_size,
                          int verify_checksums);
 
+/* Frame decode for ordinary (pageable) host memory, staged through the context's pinned bounce buffers with
+ * H2D / decode / D2H and the host copies overlapped.  Source bytes come from h_src (absolute offsets, like the
+ * jobs' src_off) or, when `fetch` is given, from fetch(fetch_ctx, dst, len, offset) (ZXC_OK or a negative code):
+ * the reader path of zxc_seekable (include/zxc_seekable.h:96-140).  Decoded bytes [clip_lo, clip_hi) (job dst
+ * coordinates) land at h_dst. */
+typedef int (*zxg_fetch_fn)(void* ctx, void* dst, size_t len, uint64_t off);
+int zxg_decode_staged(zxg_ctx* c, const uint8_t* h_src, zxg_fetch_fn fetch, void* fetch_ctx, uint64_t src_lo,
+                      uint64_t src_hi, uint8_t* h_dst, uint64_t clip_lo, uint64_t clip_hi, const zxc_b200_job_t* h_jobs,
+                      uint32_t n_jobs, int32_t* h_status, const void* h_dict, uint32_t dict_size, const void* h_dict_huf,
+                      uint32_t block_size, int verify_checksums);
+
 #ifdef __cplusplus
 }
 #endif
