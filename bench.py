@@ -59,6 +59,19 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def dram_traffic(decoded_bytes):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the decode kernel, per launch: taken from the committed ncu
+    capture (profiles/r02_decode_traffic.json, written from the --set full capture named inside it) and scaled to this
+    launch's decoded bytes (the capture decodes a shorter frame of the same corpus)."""
+    p = os.path.join(ROOT, "profiles", "r02_decode_traffic.json")
+    try:
+        t = json.load(open(p))
+        per_byte = (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["decoded_bytes"]
+        return int(per_byte * decoded_bytes), f"profiles/r02_decode_traffic.json <- {t['source']}"
+    except Exception:
+        return None, "no committed capture"
+
+
 class ClockSampler:
     """SM clock and throttle reasons during the timed region (B200_PROFILING.md recipe).  NVML is polled
     every 2 ms from a thread (the timed region is ~0.15 s, too short for nvidia-smi's 100 ms loop);
@@ -559,6 +572,25 @@ def main():
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_value = (n * world) / float(t_e.item()) / 1e9
 
+    # ---- the same call with ordinary (pageable) numpy buffers: what an existing libzxc caller passes in
+    p_out = np.zeros(n, dtype=np.uint8)  # pre-faulted
+    r = prod.lib.zxc_decompress(frame.ctypes.data, frame.size, p_out.ctypes.data, n, None)
+    assert r == n, r
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        r = prod.lib.zxc_decompress(frame.ctypes.data, frame.size, p_out.ctypes.data, n, None)
+    pg_dt = (time.perf_counter() - t0) / 2
+    assert r == n
+    if not args.no_verify:
+        assert np.array_equal(p_out, data), "pageable e2e output differs"
+    del p_out
+    t_p = torch.tensor([pg_dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_p, op=dist.ReduceOp.MAX)
+    e2e_pageable = (n * world) / float(t_p.item()) / 1e9
+
     # ---- supplementary: NVLink gather of decoded output (N > 1), bounded slice
     gather = None
     if world > 1:
@@ -586,6 +618,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak()
+        traffic, traffic_src = dram_traffic(n)
         avg_launch_ms = float(np.mean(per_launch_ms))
         achieved = algo_bytes / (avg_launch_ms * 1e-3) / 1e9
         line = {"metric": "decompress GB/s (uncompressed)", "value": round(value, 2), "unit": "GB/s",
@@ -593,13 +626,18 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": config,
                 "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                             "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                             "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
+                             "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": algo_bytes, "compressed_bytes": comp_bytes,
-                             "decoded_bytes": n, "kernel": "zxc_decode_kernel", "avg_launch_ms": round(avg_launch_ms, 4),
+                             "decoded_bytes": n, "kernel": "zxc_decode_kernel<false,false> (sequence-centric body)",
+                             "avg_launch_ms": round(avg_launch_ms, 4),
                              "decoded_only_frac": round((n / (avg_launch_ms * 1e-3) / 1e9) / peak, 4)},
                 "e2e": {"value": round(e2e_value, 2), "unit": "GB/s", "h2d_bytes_per_step": int(frame.size),
                         "d2h_bytes_per_step": int(n), "api": "zxc_decompress(host frame, host dst), pinned host buffers",
                         "steps": e2e_steps},
+                "e2e_pageable": {"value": round(e2e_pageable, 2), "unit": "GB/s",
+                                 "api": "zxc_decompress(host frame, host dst), ordinary pageable buffers (staged through the "
+                                        "library's NUMA-local pinned bounce buffers and copy pool)"},
                 "gpu_launches": launches, "clocks": clocks, "ratio": round(frame.size / n, 4), "blocks_per_gpu": int(nb),
                 "prep": prep}
         if gather:

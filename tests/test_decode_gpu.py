@@ -260,3 +260,33 @@ def test_huffman_sections(prod, ref, orc):
         assert (r0 < 0) == (r1 < 0), (t, pos, r0, r1)
         if r0 >= 0:
             assert r0 == r1 and np.array_equal(o0, o1)
+
+
+def test_frames_with_short_non_final_blocks(prod, ref):
+    """The reference decoder accepts any split into blocks of at most block_size (zxc_dispatch.c:912-1001); its
+    encoder never emits one, so the frame is stitched from single-block frames of irregular pieces."""
+    import struct
+    data = zc.silesia_shaped(1 << 20, seed=21)[:400000]
+    bs = 65536
+    rng = np.random.default_rng(4)
+    for level in (1, 3, 6):
+        cuts, p = [], 0
+        while p < data.size:
+            n = int(rng.integers(1, bs + 1)) if len(cuts) % 3 else bs  # mix of full and short blocks
+            cuts.append((p, min(data.size, p + n)))
+            p += n
+        head, eof, blocks = None, None, []
+        for a, b in cuts:
+            fr = ref.compress(data[a:b], level=level, block_size=bs).tobytes()
+            head, eof = fr[:16], fr[-20:-12]
+            blocks.append(fr[16:-20])
+        frame = np.frombuffer(head + b"".join(blocks) + eof + struct.pack("<QI", data.size, 0), np.uint8)
+        r0, o0 = ref.decompress(frame, data.size)
+        assert r0 == data.size and np.array_equal(o0, data), ("reference", level, r0)
+        r1, o1 = prod.decompress(frame, data.size)
+        assert r1 == data.size, (level, z.ERR.get(r1, r1))
+        assert np.array_equal(o1, data), level
+        # exact verdicts on capacity: one byte short fails the same way in both
+        r0s, _ = ref.decompress(frame, data.size - 1)
+        r1s, _ = prod.decompress(frame, data.size - 1)
+        assert r0s == r1s, (level, r0s, r1s)

@@ -353,6 +353,67 @@ static int64_t first_failure(const int32_t* st, const zxc_b200_job_t* jobs, size
     return 0;
 }
 
+/* Frames whose non-final blocks decode to less than block_size.  The reference's encoder never emits one, but
+ * its decoder accepts any split (zxc_dispatch.c:912-1001: every block is decoded on its own and appended), so
+ * this build does too: one pass over all blocks to learn their sizes (each into its own block_size slot), the
+ * reference's verdict order over those sizes (first failing block, then capacity), then a second pass that
+ * decodes every block at its true offset.  Only reached after the regular plan saw a size mismatch. */
+static int64_t decompress_frame_any_split(zxg_ctx* g, const uint8_t* src, const zxw_walk_t* w, uint8_t* dst,
+                                          size_t dst_capacity, const uint8_t* dict, size_t dict_size,
+                                          const uint8_t* dict_huf, int verify, uint64_t* produced_out) {
+    const size_t n = w->n_jobs;
+    const uint32_t bs = w->block_size;
+    zxc_b200_job_t* jobs = (zxc_b200_job_t*)malloc(n * sizeof *jobs);
+    int32_t* st = (int32_t*)malloc(n * sizeof *st);
+    int64_t ret = ZXC_OK;
+    if (!jobs || !st) { ret = ZXC_ERROR_MEMORY; goto out; }
+    const uint64_t src_lo = w->jobs[0].src_off, src_hi = w->jobs[n - 1].src_off + w->jobs[n - 1].src_len;
+    uint8_t* d_in = (uint8_t*)zxg_buffer(g, ZXG_BUF_IN, (size_t)(src_hi - src_lo) + 16);
+    if (!d_in) { ret = ZXC_ERROR_MEMORY; goto out; }
+    int rc = zxg_h2d(g, d_in, src + src_lo, (size_t)(src_hi - src_lo));
+    if (rc != ZXC_OK) { ret = rc; goto out; }
+    /* pass 1: sizes, a window of blocks at a time (the bytes are thrown away) */
+    const size_t win = ((size_t)256 << 20) / bs ? ((size_t)256 << 20) / bs : 1;
+    for (size_t i0 = 0; i0 < n; i0 += win) {
+        const size_t cnt = n - i0 < win ? n - i0 : win;
+        uint8_t* d_tmp = (uint8_t*)zxg_buffer(g, ZXG_BUF_OUT, cnt * (size_t)bs + 16);
+        if (!d_tmp) { ret = ZXC_ERROR_MEMORY; goto out; }
+        for (size_t k = 0; k < cnt; k++) {
+            jobs[i0 + k] = w->jobs[i0 + k];
+            jobs[i0 + k].dst_off = (uint64_t)k * bs;
+            jobs[i0 + k].dst_cap = bs;
+        }
+        rc = zxg_decode_jobs(g, d_in - src_lo, d_tmp, jobs + i0, (uint32_t)cnt, st + i0, dict, (uint32_t)dict_size, dict_huf, bs,
+                             verify);
+        if (rc != ZXC_OK) { ret = rc; goto out; }
+    }
+    /* the reference's order: a block's own error first, then whether it still fits */
+    uint64_t op = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (st[i] < 0) { ret = st[i]; goto out; }
+        if ((uint64_t)st[i] > dst_capacity - op) { ret = ZXC_ERROR_DST_TOO_SMALL; goto out; }
+        jobs[i].dst_off = op;
+        jobs[i].dst_cap = (uint32_t)st[i];
+        op += (uint64_t)st[i];
+    }
+    /* pass 2: every block at its true offset */
+    if (op > 0) {
+        uint8_t* d_out = (uint8_t*)zxg_buffer(g, ZXG_BUF_OUT, (size_t)op + 16);
+        if (!d_out) { ret = ZXC_ERROR_MEMORY; goto out; }
+        rc = zxg_decode_jobs(g, d_in - src_lo, d_out, jobs, (uint32_t)n, st, dict, (uint32_t)dict_size, dict_huf, bs, verify);
+        if (rc != ZXC_OK) { ret = rc; goto out; }
+        for (size_t i = 0; i < n; i++)
+            if (st[i] < 0 || (uint32_t)st[i] != jobs[i].dst_cap) { ret = st[i] < 0 ? st[i] : ZXC_ERROR_CORRUPT_DATA; goto out; }
+        rc = zxg_d2h(g, dst, d_out, (size_t)op);
+        if (rc != ZXC_OK) { ret = rc; goto out; }
+    }
+    *produced_out = op;
+out:
+    free(jobs);
+    free(st);
+    return ret;
+}
+
 static int64_t decompress_frame(zxg_ctx* g, const uint8_t* src, size_t src_size, uint8_t* dst,
                                 size_t dst_capacity, const zxc_decompress_opts_t* opts) {
     const int checksum_enabled = opts ? opts->checksum_enabled : 0;
@@ -400,6 +461,7 @@ static int64_t decompress_frame(zxg_ctx* g, const uint8_t* src, size_t src_size,
             if (prc != ZXC_OK) { ret = prc; goto out; }
             int mm = 0;
             const int64_t pf = first_failure(status, w.jobs, n_fit, &mm);
+            if (pf < 0 && mm) goto any_split;
             if (pf < 0) { ret = pf; goto out; }
             goto decoded;
         }
@@ -410,6 +472,7 @@ static int64_t decompress_frame(zxg_ctx* g, const uint8_t* src, size_t src_size,
             if (prc != ZXC_OK) { ret = prc; goto out; }
             int mm = 0;
             const int64_t pf = first_failure(status, w.jobs, n_fit, &mm);
+            if (pf < 0 && mm) goto any_split;
             if (pf < 0) { ret = pf; goto out; }
             goto decoded;
         }
@@ -425,9 +488,19 @@ static int64_t decompress_frame(zxg_ctx* g, const uint8_t* src, size_t src_size,
          * reference's own order: first block error, else capacity, else footer */
         int mismatch = 0;
         const int64_t ff = first_failure(status, w.jobs, n_fit, &mismatch);
+        if (ff < 0 && mismatch) goto any_split;
         if (ff < 0) { ret = ff; goto out; }
         rc = zxg_d2h(g, dst, d_out, (size_t)produced);
         if (rc != ZXC_OK) { ret = rc; goto out; }
+    }
+    if (n_fit < w.n_jobs && w.end == ZXW_END_EOF && w.footer_size <= dst_capacity) goto any_split; /* short blocks may fit */
+    if (0) {
+    any_split:; /* a block decoded to something other than its planned size: general split (see above) */
+        uint64_t p2 = 0;
+        const int64_t r2 = decompress_frame_any_split(g, src, &w, dst, dst_capacity, dict, dict_size, dict_huf, verify, &p2);
+        if (r2 < 0) { ret = r2; goto out; }
+        produced = p2;
+        n_fit = w.n_jobs;
     }
 decoded:
     if (n_fit < w.n_jobs) { ret = ZXC_ERROR_DST_TOO_SMALL; goto out; }

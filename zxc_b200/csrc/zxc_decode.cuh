@@ -609,6 +609,33 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
     w.near_lo = 0;
     u32 O = 0, L = 0, F = 0, epos = 0, ring_lo = 0;
 
+    /* Escape values for the whole block up front (segment-map scan over the extras section, zxc_decode2_core.h):
+     * a batch then reads its values by ordinal instead of walking the varint chain lane-uniformly.  The values
+     * live in the rank-table area of the scratch, idle once the sections are parsed; a section too long for it
+     * keeps the per-batch walk. */
+    u32* vals = reinterpret_cast<u32*>(scratch + scr_lit_cap(scratch_cap) + scr_tok_cap(scratch_cap) + (u32)HUF_WORK_BYTES);
+    const bool use_vals = ext_end != 0u && 4ull * ext_end <= scr_cum_cap(scratch_cap);
+    u32 n_val = 0, ord_base = 0;
+    if (use_vals) {
+        const u32 seg = max(4u, (ext_end + 31u) / 32u);
+        const u32 nseg = (ext_end + seg - 1u) / seg;
+        const u32 lo = lane * seg, hi = min(ext_end, lo + seg);
+        u64 inc = lane < nseg ? z2_seg_map(ext, lo, hi, ext_end) : Z2_MAP_ID;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            const u64 o = __shfl_up_sync(FULL, inc, dd);
+            if (lane >= (u32)dd) inc = z2_map_compose(o, inc);
+        }
+        u64 excl = __shfl_up_sync(FULL, inc, 1);
+        if (lane == 0) excl = Z2_MAP_ID;
+        n_val = z2_map_cnt(__shfl_sync(FULL, inc, 31), 0);
+        if (lane < nseg) {
+            const u32 ent = z2_map_exit(excl, 0);
+            if (ent != 3u) z2_seg_values(ext, lo, hi, ext_end, ent, z2_map_cnt(excl, 0), vals);
+        }
+        __syncwarp();
+    }
+
     u32 base = 0;
     while (base < n_seq) {
         /* ---- unpack tokens and offsets ---- */
@@ -637,7 +664,14 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
         const bool e_ll = valid && ll == esc, e_ml = valid && ml == esc;
         const u32 m_ll = __ballot_sync(FULL, e_ll), m_ml = __ballot_sync(FULL, e_ml);
         u32 k_esc = 0, epos_end = epos;
-        if (m_ll | m_ml) {
+        if ((m_ll | m_ml) && use_vals) {
+            u32 k = ord_base + __popc(m_ll & lt_mask) + __popc(m_ml & lt_mask);
+            if (e_ll) {
+                ll += k < n_val ? vals[k] : 0u; /* past the last varint the reference reads 0 (:51-88) */
+                k++;
+            }
+            if (e_ml) ml += k < n_val ? vals[k] : 0u;
+        } else if (m_ll | m_ml) {
             const u32 ord_ll = __popc(m_ll & lt_mask) + __popc(m_ml & lt_mask);
             k_esc = __popc(m_ll) + __popc(m_ml);
             u32 my_pos = ext_end; /* cursor where this lane's first varint starts */
@@ -682,7 +716,9 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
             for (u32 p = ring_lo + lane; p < O; p += 32) ring[p & mask] = out[p];
             __syncwarp();
             const u32 q = ((m_ll & 1u) ? 1u : 0u) + ((m_ml & 1u) ? 1u : 0u);
-            for (u32 s = 0; s < q; s++) epos = varint_advance(ext, epos, ext_end); /* rare: re-walk */
+            ord_base += q;
+            if (!use_vals)
+                for (u32 s = 0; s < q; s++) epos = varint_advance(ext, epos, ext_end); /* rare: re-walk */
             base += 1;
             continue;
         }
@@ -794,9 +830,12 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
         if (m < nvalid) {
             const u32 below = (1u << m) - 1u;
             const u32 q = __popc(m_ll & below) + __popc(m_ml & below);
-            for (u32 s = 0; s < q; s++) epos = varint_advance(ext, epos, ext_end); /* rare: re-walk */
+            ord_base += q;
+            if (!use_vals)
+                for (u32 s = 0; s < q; s++) epos = varint_advance(ext, epos, ext_end); /* rare: re-walk */
             base += m;
         } else {
+            ord_base += __popc(m_ll) + __popc(m_ml);
             epos = epos_end;
             base += 32;
         }

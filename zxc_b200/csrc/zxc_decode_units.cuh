@@ -248,7 +248,10 @@ __device__ __noinline__ int decode_lz_units(const u8* lit, u32 n_lit_avail, cons
                 const u8* sp = is_lit ? lit + ((i32)pos - cM) : (s0 >= 0 ? out + s0 : dict + ((i32)dict_size + s0));
                 u32 w0, w1, w2, w3;
                 uw_read16(sp - d, d, d + n, w0, w1, w2, w3);
-                const u32 m0 = uw_lowmask(d, 0), m1 = uw_lowmask(d, 1), m2 = uw_lowmask(d, 2), m3 = uw_lowmask(d, 3);
+                /* bytes below unit offset d keep what earlier pieces put there: a 128-bit mask from two 64-bit shifts */
+                const u64 lo64 = d >= 8u ? ~0ull : ((1ull << (8u * d)) - 1ull);
+                const u64 hi64 = d <= 8u ? 0ull : ((1ull << (8u * (d - 8u))) - 1ull);
+                const u32 m0 = (u32)lo64, m1 = (u32)(lo64 >> 32), m2 = (u32)hi64, m3 = (u32)(hi64 >> 32);
                 a0 = (a0 & m0) | (w0 & ~m0);
                 a1 = (a1 & m1) | (w1 & ~m1);
                 a2 = (a2 & m2) | (w2 & ~m2);

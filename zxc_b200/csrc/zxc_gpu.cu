@@ -49,10 +49,11 @@ static pthread_mutex_t g_pool_mu = PTHREAD_MUTEX_INITIALIZER;
 #include <sched.h>
 #include <sys/mman.h>
 #include <sys/syscall.h>
+#include <time.h>
 #include <unistd.h>
 
 #define POOL_MAX_DEV 16
-#define POOL_MAX_THREADS 16
+#define POOL_MAX_THREADS 32
 #define POOL_SLICE ((size_t)512 << 10)
 
 struct copy_pool {
@@ -163,7 +164,7 @@ static copy_pool* pool_for_device(int dev) {
         p->have_cpus = p->numa_node >= 0 && node_cpu_set(p->numa_node, &p->cpus);
         long ncpu = p->have_cpus ? CPU_COUNT(&p->cpus) : sysconf(_SC_NPROCESSORS_ONLN);
         const char* e = getenv("ZXC_B200_COPY_THREADS");
-        int want = e ? atoi(e) : (int)(ncpu / 4);
+        int want = e ? atoi(e) : (int)(ncpu / 2);
         if (want < 2) want = 2;
         if (want > POOL_MAX_THREADS) want = POOL_MAX_THREADS;
         p->n_threads = 0;
@@ -919,6 +920,11 @@ extern "C" int zxg_decode_staged(zxg_ctx* c, const uint8_t* h_src, zxg_fetch_fn 
 
     staged_chunk ring[STAGE_SLOTS];
     uint32_t j0 = 0, issued = 0, drained = 0;
+    const int trace = getenv("ZXC_B200_STAGE_TRACE") != NULL; /* development: where the host thread's time goes */
+    double t_fill = 0, t_drain = 0, t_wait_in = 0, t_wait_out = 0, t_launch = 0;
+    struct timespec ts0, ts1;
+#define STG_T0() do { if (trace) clock_gettime(CLOCK_MONOTONIC, &ts0); } while (0)
+#define STG_T1(acc) do { if (trace) { clock_gettime(CLOCK_MONOTONIC, &ts1); acc += (ts1.tv_sec - ts0.tv_sec) + 1e-9 * (ts1.tv_nsec - ts0.tv_nsec); } } while (0)
     while (rc == ZXC_OK && (drained < issued || j0 < n_jobs)) {
         if (j0 < n_jobs && issued - drained < STAGE_SLOTS) { /* a slot is free: stage and queue the next chunk */
             const int slot = (int)(issued % STAGE_SLOTS);
@@ -942,14 +948,19 @@ extern "C" int zxg_decode_staged(zxg_ctx* c, const uint8_t* h_src, zxg_fetch_fn 
             ch.c0 = o0 > clip_lo ? o0 : clip_lo;
             ch.c1 = o1 < clip_hi ? o1 : clip_hi;
             if (ch.c1 < ch.c0) ch.c1 = ch.c0;
+            STG_T0();
             cudaEventSynchronize(c->st_ev_in[slot]); /* the slot's previous H2D has left the bounce buffer */
+            STG_T1(t_wait_in);
             u8* pin = (u8*)c->st_in[slot].p;
+            STG_T0();
             if (fetch) {
                 rc = fetch(fetch_ctx, pin, (size_t)(ch.s1 - ch.s0), ch.s0);
                 if (rc != ZXC_OK) break;
             } else {
                 pool_memcpy(c->device, pin, h_src + ch.s0, (size_t)(ch.s1 - ch.s0));
             }
+            STG_T1(t_fill);
+            STG_T0();
             if (cudaMemcpyAsync(d_in + (ch.s0 - src_lo), pin, (size_t)(ch.s1 - ch.s0), cudaMemcpyHostToDevice, c->s_h2d) != cudaSuccess) {
                 rc = ZXC_B200_ERROR_CUDA;
                 break;
@@ -970,18 +981,26 @@ extern "C" int zxg_decode_staged(zxg_ctx* c, const uint8_t* h_src, zxg_fetch_fn 
             ring[slot] = ch;
             j0 = j1;
             issued++;
+            STG_T1(t_launch);
             if (j0 < n_jobs && issued - drained < STAGE_SLOTS) continue; /* fill the pipeline before draining */
         }
         /* hand the oldest finished chunk to the caller while the GPU works on the younger ones */
         const int ds = (int)(drained % STAGE_SLOTS);
+        STG_T0();
         if (cudaEventSynchronize(c->st_ev_out[ds]) != cudaSuccess) {
             rc = ZXC_B200_ERROR_CUDA;
             break;
         }
+        STG_T1(t_wait_out);
         const staged_chunk& dc = ring[ds];
+        STG_T0();
         if (dc.c1 > dc.c0) pool_memcpy(c->device, h_dst + (dc.c0 - clip_lo), c->st_out[ds].p, (size_t)(dc.c1 - dc.c0));
+        STG_T1(t_drain);
         drained++;
     }
+    if (trace)
+        fprintf(stderr, "staged decode: %u chunks; host seconds: fill %.4f, enqueue %.4f, drain %.4f, waiting for H2D slot %.4f, "
+                        "waiting for D2H %.4f\n", issued, t_fill, t_launch, t_drain, t_wait_in, t_wait_out);
     if (rc == ZXC_OK &&
         cudaMemcpyAsync(h_status, d_status, (size_t)n_jobs * sizeof(i32), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
         rc = ZXC_B200_ERROR_CUDA;
