@@ -290,3 +290,28 @@ def test_frames_with_short_non_final_blocks(prod, ref):
         r0s, _ = ref.decompress(frame, data.size - 1)
         r1s, _ = prod.decompress(frame, data.size - 1)
         assert r0s == r1s, (level, r0s, r1s)
+
+
+def test_deep_skewed_huffman_table_rank_words(prod, ref, orc):
+    """a Kraft-complete code with lengths 1,2,...,10,11,11 has eleven bitmap levels, each carrying
+    every symbol when the runs are all ones -- 11*n/8 bytes of runs, the worst case for the decoder's rank table
+    (one word per 32 run bits per node).  The table is sized for that now; the frame must decode exactly as the
+    reference decodes it."""
+    import struct
+    n = 65536
+    tmpl = ref.compress(np.zeros(n, np.uint8), level=3, block_size=n).tobytes()
+    head, eof = tmpl[:16], tmpl[-20:-12]
+    lens = bytearray(128)
+    for s, l in enumerate([1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 11]):
+        lens[s >> 1] |= l << (4 * (s & 1))
+    runs = bytes([0xFF]) * (11 * (n // 8))
+    lit = bytes(lens) + runs
+    payload = struct.pack("<IIBBBB", 0, n, 2, 0, 0, 0) + struct.pack("<I", len(lit)) + lit + bytes(32)
+    hdr = bytearray(struct.pack("<BBB", 1, 0, 0) + struct.pack("<I", len(payload)) + b"\0")
+    hdr[7] = orc.lib.zxo_hash8(bytes(hdr))
+    frame = np.frombuffer(head + bytes(hdr) + payload + eof + struct.pack("<QI", n, 0), np.uint8)
+    r0, o0 = ref.decompress(frame, n)
+    r1, o1 = prod.decompress(frame, n)
+    assert r1 == r0, (r0, z.ERR.get(r1, r1))
+    if r0 == n:
+        assert np.array_equal(o0, o1) and int(o1[0]) == 11 and int(o1.min()) == int(o1.max())

@@ -38,16 +38,8 @@ __device__ __forceinline__ z2_rec_t uw_ld_rec(const z2_rec_t* rec, u32 i) {
     return r;
 }
 
-/* 16 bytes starting at byte address p (any alignment); only the vectors that hold bytes [lo, hi) of the
- * result are loaded, so nothing outside the source range is touched */
-__device__ __forceinline__ void uw_read16(const u8* p, u32 lo, u32 hi, u32& w0, u32& w1, u32& w2, u32& w3) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    const u32 sh = (u32)(a & 15u);
-    const uint4* q = reinterpret_cast<const uint4*>(a - sh);
-    uint4 A = make_uint4(0, 0, 0, 0), B = make_uint4(0, 0, 0, 0);
-    if (sh + lo < 16u) A = q[0];
-    if (sh + hi > 16u) B = q[1];
-    /* words V[0..7] = A.x .. B.w; wanted: bytes sh .. sh+15 */
+/* bytes sh .. sh+15 of the 32 bytes A:B (sh < 16): a two-stage word barrel and four funnel shifts */
+__device__ __forceinline__ void uw_extract16(uint4 A, uint4 B, u32 sh, u32& w0, u32& w1, u32& w2, u32& w3) {
     const bool s1 = (sh & 4u) != 0u, s2 = (sh & 8u) != 0u;
     const u32 x0 = s1 ? A.y : A.x, x1 = s1 ? A.z : A.y, x2 = s1 ? A.w : A.z, x3 = s1 ? B.x : A.w, x4 = s1 ? B.y : B.x,
               x5 = s1 ? B.z : B.y, x6 = s1 ? B.w : B.z;
@@ -57,6 +49,30 @@ __device__ __forceinline__ void uw_read16(const u8* p, u32 lo, u32 hi, u32& w0, 
     w1 = __funnelshift_r(y1, y2, bs);
     w2 = __funnelshift_r(y2, y3, bs);
     w3 = __funnelshift_r(y3, y4, bs);
+}
+/* 128-bit value x3:x2:x1:x0 shifted left by k bytes (0..16), zeros shifted in */
+__device__ __forceinline__ void uw_shl128(u32& x0, u32& x1, u32& x2, u32& x3, u32 k) {
+    const u32 ws = k >> 2, bs = (k & 3u) * 8u;
+    const u32 y3 = ws == 0 ? x3 : ws == 1 ? x2 : ws == 2 ? x1 : ws == 3 ? x0 : 0u;
+    const u32 y2 = ws == 0 ? x2 : ws == 1 ? x1 : ws == 2 ? x0 : 0u;
+    const u32 y1 = ws == 0 ? x1 : ws == 1 ? x0 : 0u;
+    const u32 y0 = ws == 0 ? x0 : 0u;
+    x3 = __funnelshift_l(y2, y3, bs);
+    x2 = __funnelshift_l(y1, y2, bs);
+    x1 = __funnelshift_l(y0, y1, bs);
+    x0 = y0 << bs;
+}
+
+/* 16 bytes starting at byte address p (any alignment); only the vectors that hold bytes [lo, hi) of the
+ * result are loaded, so nothing outside the source range is touched */
+__device__ __forceinline__ void uw_read16(const u8* p, u32 lo, u32 hi, u32& w0, u32& w1, u32& w2, u32& w3) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const u32 sh = (u32)(a & 15u);
+    const uint4* q = reinterpret_cast<const uint4*>(a - sh);
+    uint4 A = make_uint4(0, 0, 0, 0), B = make_uint4(0, 0, 0, 0);
+    if (sh + lo < 16u) A = q[0];
+    if (sh + hi > 16u) B = q[1];
+    uw_extract16(A, B, sh, w0, w1, w2, w3);
 }
 
 /* mask of the bytes of word j (bytes 4j..4j+3 of the unit) that lie below unit offset d */
@@ -256,6 +272,34 @@ __device__ __noinline__ int decode_lz_units(const u8* lit, u32 n_lit_avail, cons
                 a1 = (a1 & m1) | (w1 & ~m1);
                 a2 = (a2 & m2) | (w2 & ~m2);
                 a3 = (a3 & m3) | (w3 & ~m3);
+            } else if (s0 >= 0 && out16) {
+                /* distance below 16 inside the window: the piece repeats the `coff` bytes in front of it.  Take the
+                 * 16 bytes that end at pos (previous unit : own registers), keep the last `coff`, double the run
+                 * until it covers a unit, and put it behind the bytes the unit already has. */
+                const u32 u0 = u << 4;
+                uint4 Pv = make_uint4(0, 0, 0, 0);
+                if (s0 < (i32)u0) Pv = *reinterpret_cast<const uint4*>(out + u0 - 16u);
+                u32 h0, h1, h2, h3;
+                uw_extract16(Pv, make_uint4(a0, a1, a2, a3), d, h0, h1, h2, h3);
+                /* pattern = bytes 16-coff .. 15 of h, moved to the bottom (a right shift by 16-coff bytes) */
+                u32 x0, x1, x2, x3;
+                uw_extract16(make_uint4(h0, h1, h2, h3), make_uint4(0, 0, 0, 0), 16u - (u32)coff, x0, x1, x2, x3);
+#pragma unroll 1
+                for (u32 len = (u32)coff; len < 16u; len <<= 1) {
+                    u32 y0 = x0, y1 = x1, y2 = x2, y3 = x3;
+                    uw_shl128(y0, y1, y2, y3, len);
+                    x0 |= y0;
+                    x1 |= y1;
+                    x2 |= y2;
+                    x3 |= y3;
+                }
+                uw_shl128(x0, x1, x2, x3, d);
+                const u64 lo64 = d >= 8u ? ~0ull : ((1ull << (8u * d)) - 1ull);
+                const u64 hi64 = d <= 8u ? 0ull : ((1ull << (8u * (d - 8u))) - 1ull);
+                a0 = (a0 & (u32)lo64) | x0;
+                a1 = (a1 & (u32)(lo64 >> 32)) | x1;
+                a2 = (a2 & (u32)hi64) | x2;
+                a3 = (a3 & (u32)(hi64 >> 32)) | x3;
             } else {
                 const u32 u0 = u << 4;
 #pragma unroll 1

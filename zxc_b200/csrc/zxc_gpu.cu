@@ -160,15 +160,16 @@ static copy_pool* pool_for_device(int dev) {
         pthread_mutex_init(&p->mu, NULL);
         pthread_cond_init(&p->cv_go, NULL);
         pthread_cond_init(&p->cv_done, NULL);
-        p->numa_node = device_numa_node(dev);
+        const int async_pool = dev >= POOL_MAX_DEV / 2;
+        p->numa_node = device_numa_node(async_pool ? dev - POOL_MAX_DEV / 2 : dev);
         p->have_cpus = p->numa_node >= 0 && node_cpu_set(p->numa_node, &p->cpus);
         long ncpu = p->have_cpus ? CPU_COUNT(&p->cpus) : sysconf(_SC_NPROCESSORS_ONLN);
         const char* e = getenv("ZXC_B200_COPY_THREADS");
-        int want = e ? atoi(e) : (int)(ncpu / 2);
+        int want = e ? atoi(e) : (int)(ncpu / 4); /* per pool: a quarter of the node's CPUs fill, a quarter drain */
         if (want < 2) want = 2;
         if (want > POOL_MAX_THREADS) want = POOL_MAX_THREADS;
         p->n_threads = 0;
-        for (int t = 0; t < want - 1; t++) /* the caller is the last member of every job */
+        for (int t = 0; t < want - (async_pool ? 0 : 1); t++) /* a synchronous job counts its caller as a member */
             if (pthread_create(&p->th[p->n_threads], NULL, pool_worker, p) == 0) p->n_threads++;
         __atomic_store_n(&p->started, 1, __ATOMIC_RELEASE);
     }
@@ -176,11 +177,41 @@ static copy_pool* pool_for_device(int dev) {
     return p;
 }
 
+/* asynchronous variant on the device's second pool (workers only): pool_copy_begin returns at once,
+ * pool_copy_end waits for the copy -- lets the caller's drain overlap its next fill */
+static copy_pool* pool_copy_begin(int dev, void* dst, const void* src, size_t n) {
+    if (dev < 0 || dev >= POOL_MAX_DEV / 2) dev = 0;
+    copy_pool* p = pool_for_device(dev + POOL_MAX_DEV / 2);
+    if (p->n_threads == 0 || n < ((size_t)2 << 20)) {
+        memcpy(dst, src, n);
+        return NULL;
+    }
+    pthread_mutex_lock(&p->job_mu);
+    pthread_mutex_lock(&p->mu);
+    p->d = (u8*)dst;
+    p->s = (const u8*)src;
+    p->bytes = n;
+    p->next = 0;
+    p->busy = p->n_threads;
+    p->gen++;
+    pthread_cond_broadcast(&p->cv_go);
+    pthread_mutex_unlock(&p->mu);
+    return p;
+}
+static void pool_copy_end(copy_pool* p) {
+    if (!p) return;
+    pthread_mutex_lock(&p->mu);
+    while (p->busy) pthread_cond_wait(&p->cv_done, &p->mu);
+    pthread_mutex_unlock(&p->mu);
+    pthread_mutex_unlock(&p->job_mu);
+}
+
 static void pool_memcpy(int dev, void* dst, const void* src, size_t n) {
     if (n < ((size_t)2 << 20)) {
         memcpy(dst, src, n);
         return;
     }
+    if (dev < 0 || dev >= POOL_MAX_DEV / 2) dev = 0;
     copy_pool* p = pool_for_device(dev);
     pthread_mutex_lock(&p->job_mu);
     pthread_mutex_lock(&p->mu);
@@ -210,24 +241,20 @@ static int pinned_alloc(pinned_buf* b, size_t bytes, int node) {
     b->p = NULL;
     b->bytes = bytes;
     b->mapped = 0;
+    /* the driver allocates in the calling task's context: a preferred-node policy around the call puts the pages
+     * next to the GPU; cudaMallocHost memory also DMAs faster than a registered 4 KiB-page mapping (measured) */
+    int policy_set = 0;
+#ifdef SYS_set_mempolicy
     if (node >= 0 && node < 64) {
-        void* m = mmap(NULL, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
-        if (m != MAP_FAILED) {
-            unsigned long mask = 1ul << node;
-#ifdef SYS_mbind
-            syscall(SYS_mbind, m, bytes, 1 /* MPOL_PREFERRED */, &mask, sizeof(mask) * 8, 0);
-#endif
-            memset(m, 0, bytes);
-            if (cudaHostRegister(m, bytes, cudaHostRegisterDefault) == cudaSuccess) {
-                b->p = m;
-                b->mapped = 1;
-                return ZXC_OK;
-            }
-            cudaGetLastError();
-            munmap(m, bytes);
-        }
+        unsigned long mask = 1ul << node;
+        policy_set = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, &mask, sizeof(mask) * 8) == 0;
     }
-    if (cudaMallocHost(&b->p, bytes) != cudaSuccess) {
+#endif
+    const cudaError_t e = cudaMallocHost(&b->p, bytes);
+#ifdef SYS_set_mempolicy
+    if (policy_set) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, NULL, 0);
+#endif
+    if (e != cudaSuccess) {
         b->p = NULL;
         return ZXC_ERROR_MEMORY;
     }
@@ -244,7 +271,7 @@ static void pinned_free(pinned_buf* b) {
     b->p = NULL;
 }
 
-#define STAGE_SLOTS 3
+#define STAGE_SLOTS 4
 #define EV_RING 8
 
 struct zxg_ctx {
@@ -257,6 +284,7 @@ struct zxg_ctx {
     unsigned long long* counter; /* [0..1] work counters, [2] deferred-job counter */
     unsigned long long* reduce_out; /* device: [0] first bad index, [1] byte sum (zxc_b200_reduce_status) */
     cudaStream_t s_h2d, s_d2h;   /* copy engines for the pipelined frame paths (lazily created) */
+    cudaStream_t s_dec[STAGE_SLOTS]; /* staged path: chunk decodes overlap (a 512-block launch is latency-bound) */
     cudaEvent_t ev_ring[EV_RING]; /* reused by the pipelines: no event is created per chunk */
     pinned_buf st_in[STAGE_SLOTS], st_out[STAGE_SLOTS]; /* staging for pageable callers (lazily allocated) */
     cudaEvent_t st_ev_in[STAGE_SLOTS], st_ev_dec[STAGE_SLOTS], st_ev_out[STAGE_SLOTS];
@@ -309,11 +337,11 @@ extern "C" zxg_ctx* zxg_create(void) {
     if (!c) return NULL;
     cudaGetDevice(&c->device);
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc((void**)&c->counter, 8 * sizeof(unsigned long long)) != cudaSuccess) {
+        cudaMalloc((void**)&c->counter, 32 * sizeof(unsigned long long)) != cudaSuccess) {
         free(c);
         return NULL;
     }
-    c->reduce_out = c->counter + 4;
+    c->reduce_out = c->counter + 28;
     c->numa_node = device_numa_node(c->device);
     int smc = 0;
     if (cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, c->device) != cudaSuccess || smc <= 0) smc = g_sm_count;
@@ -340,6 +368,8 @@ extern "C" void zxg_destroy(zxg_ctx* c) {
     for (int i = 0; i < EV_RING; i++)
         if (c->ev_ring[i]) cudaEventDestroy(c->ev_ring[i]);
     cudaFree(c->counter);
+    for (int i = 0; i < STAGE_SLOTS; i++)
+        if (c->s_dec[i]) cudaStreamDestroy(c->s_dec[i]);
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
     cudaStreamDestroy(c->stream);
@@ -877,6 +907,8 @@ static int staged_ready(zxg_ctx* c) {
     }
     if (!c->s_h2d && cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking) != cudaSuccess) return ZXC_B200_ERROR_CUDA;
     if (!c->s_d2h && cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking) != cudaSuccess) return ZXC_B200_ERROR_CUDA;
+    for (int i = 0; i < STAGE_SLOTS; i++)
+        if (!c->s_dec[i] && cudaStreamCreateWithFlags(&c->s_dec[i], cudaStreamNonBlocking) != cudaSuccess) return ZXC_B200_ERROR_CUDA;
     c->st_ready = 1;
     return ZXC_OK;
 }
@@ -892,6 +924,8 @@ extern "C" int zxg_decode_staged(zxg_ctx* c, const uint8_t* h_src, zxg_fetch_fn 
                                  const zxc_b200_job_t* h_jobs, uint32_t n_jobs, int32_t* h_status, const void* h_dict,
                                  uint32_t dict_size, const void* h_dict_huf, uint32_t block_size, int verify_checksums) {
     if (n_jobs == 0) return ZXC_OK;
+    struct timespec tw0, tw1, tw2;
+    clock_gettime(CLOCK_MONOTONIC, &tw0);
     int rc = staged_ready(c);
     if (rc != ZXC_OK) return rc;
     const uint64_t produced = h_jobs[n_jobs - 1].dst_off + h_jobs[n_jobs - 1].dst_cap;
@@ -899,8 +933,26 @@ extern "C" int zxg_decode_staged(zxg_ctx* c, const uint8_t* h_src, zxg_fetch_fn 
     u8* d_out = (u8*)zxg_buffer(c, ZXG_BUF_OUT, (size_t)produced + 16);
     zxc_b200_job_t* d_jobs = (zxc_b200_job_t*)zxg_buffer(c, ZXG_BUF_JOBS, (size_t)n_jobs * sizeof(zxc_b200_job_t));
     i32* d_status = (i32*)zxg_buffer(c, ZXG_BUF_STATUS, (size_t)n_jobs * sizeof(i32));
-    const size_t scratch_size = launch_scratch_bytes(n_jobs, block_size);
-    void* d_scratch = zxg_buffer(c, ZXG_BUF_SCRATCH, scratch_size);
+    /* a chunk holds at most STAGE_OUT / (smallest decoded block) jobs; every slot decodes on its own stream with its
+     * own scratch region and work counters, so up to STAGE_SLOTS chunk launches are resident together */
+    uint32_t chunk_jobs_max = 1;
+    {
+        uint32_t j = 0;
+        while (j < n_jobs) {
+            uint32_t j1 = j;
+            uint64_t ao = 0, ai = 0;
+            while (j1 < n_jobs && ao + h_jobs[j1].dst_cap <= STAGE_OUT && ai + h_jobs[j1].src_len <= STAGE_IN) {
+                ao += h_jobs[j1].dst_cap;
+                ai += h_jobs[j1].src_len;
+                j1++;
+            }
+            if (j1 == j) break;
+            if (j1 - j > chunk_jobs_max) chunk_jobs_max = j1 - j;
+            j = j1;
+        }
+    }
+    const size_t scratch_size = (launch_scratch_bytes(chunk_jobs_max, block_size) + 255) & ~(size_t)255;
+    u8* d_scratch = (u8*)zxg_buffer(c, ZXG_BUF_SCRATCH, scratch_size * STAGE_SLOTS);
     if (!d_in || !d_out || !d_jobs || !d_status || !d_scratch) return ZXC_ERROR_MEMORY;
     u8* d_dict = NULL;
     u8* d_huf = NULL;
@@ -920,13 +972,21 @@ extern "C" int zxg_decode_staged(zxg_ctx* c, const uint8_t* h_src, zxg_fetch_fn 
 
     staged_chunk ring[STAGE_SLOTS];
     uint32_t j0 = 0, issued = 0, drained = 0;
+    copy_pool* drain_job = NULL; /* the drain in flight on the second pool ... */
+    int drain_slot = -1;         /* ... and the output slot it is reading */
     const int trace = getenv("ZXC_B200_STAGE_TRACE") != NULL; /* development: where the host thread's time goes */
     double t_fill = 0, t_drain = 0, t_wait_in = 0, t_wait_out = 0, t_launch = 0;
+    cudaEvent_t tev[STAGE_SLOTS][6]; /* trace only: H2D, decode, D2H brackets of the chunk in each slot */
+    float g_h2d = 0, g_dec = 0, g_d2h = 0, g_lat = 0;
+    if (trace)
+        for (int i = 0; i < STAGE_SLOTS; i++)
+            for (int q = 0; q < 6; q++) cudaEventCreate(&tev[i][q]);
     struct timespec ts0, ts1;
 #define STG_T0() do { if (trace) clock_gettime(CLOCK_MONOTONIC, &ts0); } while (0)
 #define STG_T1(acc) do { if (trace) { clock_gettime(CLOCK_MONOTONIC, &ts1); acc += (ts1.tv_sec - ts0.tv_sec) + 1e-9 * (ts1.tv_nsec - ts0.tv_nsec); } } while (0)
     while (rc == ZXC_OK && (drained < issued || j0 < n_jobs)) {
-        if (j0 < n_jobs && issued - drained < STAGE_SLOTS) { /* a slot is free: stage and queue the next chunk */
+        /* one slot is always left to the drain in flight, so filling the next chunk never waits for it */
+        if (j0 < n_jobs && issued - drained < STAGE_SLOTS - 1) { /* a slot is free: stage and queue the next chunk */
             const int slot = (int)(issued % STAGE_SLOTS);
             staged_chunk ch;
             ch.j0 = j0;
@@ -948,6 +1008,10 @@ extern "C" int zxg_decode_staged(zxg_ctx* c, const uint8_t* h_src, zxg_fetch_fn 
             ch.c0 = o0 > clip_lo ? o0 : clip_lo;
             ch.c1 = o1 < clip_hi ? o1 : clip_hi;
             if (ch.c1 < ch.c0) ch.c1 = ch.c0;
+            if (drain_job && drain_slot == slot) { /* this chunk's D2H will overwrite what the drain is still reading */
+                pool_copy_end(drain_job);
+                drain_job = NULL;
+            }
             STG_T0();
             cudaEventSynchronize(c->st_ev_in[slot]); /* the slot's previous H2D has left the bounce buffer */
             STG_T1(t_wait_in);
@@ -961,28 +1025,35 @@ extern "C" int zxg_decode_staged(zxg_ctx* c, const uint8_t* h_src, zxg_fetch_fn 
             }
             STG_T1(t_fill);
             STG_T0();
+            if (trace) cudaEventRecord(tev[slot][0], c->s_h2d);
             if (cudaMemcpyAsync(d_in + (ch.s0 - src_lo), pin, (size_t)(ch.s1 - ch.s0), cudaMemcpyHostToDevice, c->s_h2d) != cudaSuccess) {
                 rc = ZXC_B200_ERROR_CUDA;
                 break;
             }
+            if (trace) cudaEventRecord(tev[slot][1], c->s_h2d);
             cudaEventRecord(c->st_ev_in[slot], c->s_h2d);
-            cudaStreamWaitEvent(c->stream, c->st_ev_in[slot], 0);
-            rc = launch_decode(d_in - src_lo, d_out, d_jobs + j0, j1 - j0, d_status + j0, d_dict, dict_size, d_huf, d_scratch,
-                               scratch_size, block_size, verify_checksums, c->counter, c->stream);
+            cudaStreamWaitEvent(c->s_dec[slot], c->st_ev_in[slot], 0);
+            if (trace) cudaEventRecord(tev[slot][2], c->s_dec[slot]);
+            rc = launch_decode(d_in - src_lo, d_out, d_jobs + j0, j1 - j0, d_status + j0, d_dict, dict_size, d_huf,
+                               d_scratch + (size_t)slot * scratch_size, scratch_size, block_size, verify_checksums,
+                               c->counter + 4 * slot, c->s_dec[slot]);
             if (rc != ZXC_OK) break;
-            cudaEventRecord(c->st_ev_dec[slot], c->stream);
+            if (trace) cudaEventRecord(tev[slot][3], c->s_dec[slot]);
+            cudaEventRecord(c->st_ev_dec[slot], c->s_dec[slot]);
             cudaStreamWaitEvent(c->s_d2h, c->st_ev_dec[slot], 0);
+            if (trace) cudaEventRecord(tev[slot][4], c->s_d2h);
             if (ch.c1 > ch.c0 &&
                 cudaMemcpyAsync(c->st_out[slot].p, d_out + ch.c0, (size_t)(ch.c1 - ch.c0), cudaMemcpyDeviceToHost, c->s_d2h) != cudaSuccess) {
                 rc = ZXC_B200_ERROR_CUDA;
                 break;
             }
+            if (trace) cudaEventRecord(tev[slot][5], c->s_d2h);
             cudaEventRecord(c->st_ev_out[slot], c->s_d2h);
             ring[slot] = ch;
             j0 = j1;
             issued++;
             STG_T1(t_launch);
-            if (j0 < n_jobs && issued - drained < STAGE_SLOTS) continue; /* fill the pipeline before draining */
+            if (j0 < n_jobs && issued - drained < STAGE_SLOTS - 1) continue; /* fill the pipeline before draining */
         }
         /* hand the oldest finished chunk to the caller while the GPU works on the younger ones */
         const int ds = (int)(drained % STAGE_SLOTS);
@@ -992,22 +1063,46 @@ extern "C" int zxg_decode_staged(zxg_ctx* c, const uint8_t* h_src, zxg_fetch_fn 
             break;
         }
         STG_T1(t_wait_out);
+        if (trace) {
+            float a = 0, b = 0, d2 = 0, l = 0;
+            cudaEventElapsedTime(&a, tev[ds][0], tev[ds][1]);
+            cudaEventElapsedTime(&b, tev[ds][2], tev[ds][3]);
+            cudaEventElapsedTime(&d2, tev[ds][4], tev[ds][5]);
+            cudaEventElapsedTime(&l, tev[ds][0], tev[ds][5]);
+            g_h2d += a; g_dec += b; g_d2h += d2; g_lat += l;
+        }
         const staged_chunk& dc = ring[ds];
         STG_T0();
-        if (dc.c1 > dc.c0) pool_memcpy(c->device, h_dst + (dc.c0 - clip_lo), c->st_out[ds].p, (size_t)(dc.c1 - dc.c0));
+        pool_copy_end(drain_job); /* one drain at a time; the previous one overlapped the fill above */
+        drain_job = NULL;
+        if (dc.c1 > dc.c0) drain_job = pool_copy_begin(c->device, h_dst + (dc.c0 - clip_lo), c->st_out[ds].p, (size_t)(dc.c1 - dc.c0));
+        drain_slot = ds;
         STG_T1(t_drain);
         drained++;
     }
+    clock_gettime(CLOCK_MONOTONIC, &tw1);
+    pool_copy_end(drain_job);
+    clock_gettime(CLOCK_MONOTONIC, &tw2);
     if (trace)
         fprintf(stderr, "staged decode: %u chunks; host seconds: fill %.4f, enqueue %.4f, drain %.4f, waiting for H2D slot %.4f, "
-                        "waiting for D2H %.4f\n", issued, t_fill, t_launch, t_drain, t_wait_in, t_wait_out);
+                        "waiting for D2H %.4f; loop %.4f, last drain %.4f; device ms summed over chunks: H2D %.1f decode %.1f D2H %.1f, "
+                        "H2D start to D2H end %.1f\n", issued, t_fill, t_launch, t_drain, t_wait_in, t_wait_out,
+                (tw1.tv_sec - tw0.tv_sec) + 1e-9 * (tw1.tv_nsec - tw0.tv_nsec), (tw2.tv_sec - tw1.tv_sec) + 1e-9 * (tw2.tv_nsec - tw1.tv_nsec), g_h2d, g_dec, g_d2h, g_lat);
+    if (trace)
+        for (int i = 0; i < STAGE_SLOTS; i++)
+            for (int q = 0; q < 6; q++) cudaEventDestroy(tev[i][q]);
+    cudaError_t e0 = cudaSuccess;
+    for (int i = 0; i < STAGE_SLOTS; i++) {
+        const cudaError_t e = cudaStreamSynchronize(c->s_dec[i]);
+        if (e != cudaSuccess) e0 = e;
+    }
     if (rc == ZXC_OK &&
         cudaMemcpyAsync(h_status, d_status, (size_t)n_jobs * sizeof(i32), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
         rc = ZXC_B200_ERROR_CUDA;
     const cudaError_t e1 = cudaStreamSynchronize(c->stream);
     const cudaError_t e2 = cudaStreamSynchronize(c->s_d2h);
     const cudaError_t e3 = cudaStreamSynchronize(c->s_h2d);
-    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+    if (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
         fprintf(stderr, "libzxc (B200 build): staged decode failed: %s\n", cudaGetErrorString(cudaGetLastError()));
         return ZXC_B200_ERROR_CUDA;
     }
