@@ -315,3 +315,49 @@ def test_deep_skewed_huffman_table_rank_words(prod, ref, orc):
     assert r1 == r0, (r0, z.ERR.get(r1, r1))
     if r0 == n:
         assert np.array_equal(o0, o1) and int(o1[0]) == 11 and int(o1.min()) == int(o1.max())
+
+
+_ALT_BODY = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+import zxc_corpus as zc, zxc_ctypes as z
+from test_oracle import CASES, make_case
+prod, ref = z.ZxcLib(z.PRODUCT_SO), z.ZxcLib(z.REF_SO)
+n_ok = 0
+for kind, n in CASES:
+    data = make_case(kind, n)
+    for level in (1, 3, 5, 6):
+        for bs in (4096, 65536):
+            fr = ref.compress(data, level=level, block_size=bs)
+            r, out = prod.decompress(fr, data.size)
+            assert r == data.size and np.array_equal(out, data), (kind, level, bs, r)
+            n_ok += 1
+data = zc.silesia_shaped(8 << 20, seed=33)
+fr = zc.compress_ref_mt(ref, data, level=3, block_size=65536)
+r, out = prod.decompress(fr, data.size)
+assert r == data.size and np.array_equal(out, data)
+rng = np.random.default_rng(2)
+for t in range(40):  # damaged frames: same verdict as the reference
+    f = ref.compress(data[:300000], level=3 if t & 1 else 1, block_size=65536).copy()
+    for _ in range(int(rng.integers(1, 4))):
+        f[int(rng.integers(16, f.size - 12))] = int(rng.integers(0, 256))
+    r0, o0 = ref.decompress(f, 300000)
+    r1, o1 = prod.decompress(f, 300000)
+    assert r0 == r1, (t, r0, r1)
+    if r0 > 0:
+        assert np.array_equal(o0, o1)
+print("alt-body ok", n_ok)
+"""
+
+
+@pytest.mark.parametrize("env", [{"ZXC_B200_UNITS": "1"}, {"ZXC_B200_DECODE_V2": "1"}], ids=["unit-walk-forced", "block-cooperative"])
+def test_alternative_decode_bodies_stay_bit_exact(env):
+    """The output-centric body outside its default domain and the block-cooperative kernel (off by default, DESIGN.md
+    3c) are selected by environment variables read once per process, so they run in a child process."""
+    import subprocess
+    import sys
+    e = dict(os.environ)
+    e.update(env)
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-c", _ALT_BODY % here], env=e, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "alt-body ok" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])

@@ -165,7 +165,10 @@ static copy_pool* pool_for_device(int dev) {
         p->have_cpus = p->numa_node >= 0 && node_cpu_set(p->numa_node, &p->cpus);
         long ncpu = p->have_cpus ? CPU_COUNT(&p->cpus) : sysconf(_SC_NPROCESSORS_ONLN);
         const char* e = getenv("ZXC_B200_COPY_THREADS");
-        int want = e ? atoi(e) : (int)(ncpu / 4); /* per pool: a quarter of the node's CPUs fill, a quarter drain */
+        /* per pool an eighth of the node's CPUs: measured on the 2 x 64-thread hosts, more copy threads do not help --
+         * the staged path is bound by host memory traffic (9 bytes moved per 2 decoded), and PCIe DMA slows down
+         * when 32 threads compete with it (H2D 65 -> 44 ms, D2H 73 -> 49 ms per 2 GiB going from 32 to 12 threads) */
+        int want = e ? atoi(e) : (int)(ncpu / 8);
         if (want < 2) want = 2;
         if (want > POOL_MAX_THREADS) want = POOL_MAX_THREADS;
         p->n_threads = 0;
