@@ -6,7 +6,7 @@ One "step" = one pass of the hot path (decode every block of the shard) over syn
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--gib G]
 
 Workload (BASELINE.json configs[1]): seekable ZXC frame, 64 KiB blocks, level 3, over the
-Silesia-shaped synthetic corpus (oracle/zxc_corpus.c), G GiB decoded per GPU (default 4).
+Silesia-shaped synthetic corpus (oracle/zxc_corpus.c), G GiB decoded per GPU (default 4; 8 at N = 8 = configs[4]'s 64 GiB).
 Frames are produced by the UNMODIFIED reference encoder (oracle/_ref, see BASELINE.md section 3);
 at N > 1 every rank owns the contiguous block range [rank*G GiB, (rank+1)*G GiB) of the frame
 (weak scaling: independent seekable blocks, no data-path collective).
@@ -17,8 +17,18 @@ at N > 1 every rank owns the contiguous block range [rank*G GiB, (rank+1)*G GiB)
                (pinned) buffers: H2D of the frame and D2H of the output inside the timed region.
   roofline     algorithmic bytes per launch (C + U: on-disk block bytes read once + decoded bytes
                written once) / average launch time, vs MEASURED_PEAKS.json hbm_gbs.
+  e2e_pageable the same call with ordinary (pageable) numpy buffers: the library stages them through its own
+               NUMA-local pinned bounce buffers and copy pools.
   cpu_baseline the reference's own SIMD CPU path (zxc_seekable_decompress_range_mt, all host
                threads; zxc_decompress 1 thread) on the same frame, same run, rank 0 at N=1.
+  dict         (N=1) BASELINE configs[3]: trained dictionary, 1 Mi x 4 KiB records, level 5, one frame with
+               block_size 4096 -- decode-only value + roofline, e2e through zxc_seekable_set_dict +
+               zxc_seekable_decompress_range_mt, the reference's CPU figure for the same calls.
+  encode       (N=1) BASELINE configs[2]: level 6 over 1 GiB through zxc_compress, frame compared with the reference's.
+  pipeline     (N>1) north_star's multi-GPU path from ONE seekable frame held by rank 0 (N x G GiB; 64 GiB at N=8):
+               NCCL scatter of compressed block ranges -> decode -> NCCL gather into rank 0, each phase timed on
+               the device (max over ranks), output verified on rank 0.
+  Every rank binds itself to its GPU's NUMA node before it allocates pinned host memory.
   --impl reference   times only that CPU path, same metric / config.
 """
 import argparse
