@@ -218,3 +218,47 @@ def test_buffer_api_is_callable_concurrently(prod, ref):
     for t in th:
         t.join()
     assert not errs, errs
+
+
+def test_large_unaligned_ranges_through_the_pipelines(prod, ref):
+    """Ranges of >= 32 MiB decoded take the overlapped routes: memory-backed handles with pageable
+    buffers (staged, clipped at both ends), page-locked block-aligned ranges (straight into the caller's memory), and a
+    reader-backed handle whose read_at fills the pinned input slots."""
+    import torch
+    data = zc.silesia_shaped(160 << 20, seed=6)
+    bs = 65536
+    frame = zc.compress_ref_mt(ref, data, level=3, block_size=bs)
+    L = prod.lib
+    h = L.zxc_seekable_open(frame.ctypes.data, frame.size)
+    assert h
+    rng = np.random.default_rng(8)
+    spans = [(1, data.size - 2), (bs * 3 + 17, (100 << 20) + 12345), (data.size - (40 << 20) - 7, (40 << 20) + 7)]
+    spans += [(int(rng.integers(0, 60 << 20)), int(rng.integers(33 << 20, 90 << 20))) for _ in range(3)]
+    for off, ln in spans:
+        out = np.zeros(ln, np.uint8)
+        r = L.zxc_seekable_decompress_range_mt(h, out.ctypes.data, ln, off, ln, 8)
+        assert r == ln, (off, ln, z.ERR.get(r, r))
+        assert np.array_equal(out, data[off:off + ln]), (off, ln)
+    # page-locked and block-aligned: the direct pipeline
+    h_frame = torch.from_numpy(frame).pin_memory()
+    hp = L.zxc_seekable_open(h_frame.data_ptr(), h_frame.numel())
+    ln = 96 << 20
+    pout = torch.zeros(ln, dtype=torch.uint8).pin_memory()
+    assert L.zxc_seekable_decompress_range_mt(hp, pout.data_ptr(), ln, 16 * bs, ln, 4) == ln
+    assert np.array_equal(pout.numpy(), data[16 * bs:16 * bs + ln])
+    # page-locked but ragged: staged with clipping
+    assert L.zxc_seekable_decompress_range(hp, pout.data_ptr(), ln - 5, 16 * bs + 3, ln - 5) == ln - 5
+    assert np.array_equal(pout.numpy()[:ln - 5], data[16 * bs + 3:16 * bs + 3 + ln - 5])
+    L.zxc_seekable_free(hp)
+    L.zxc_seekable_free(h)
+    # reader-backed, ragged
+    calls = []
+    rd, keep = make_reader(frame, calls)
+    L.zxc_seekable_open_reader.restype = C.c_void_p
+    L.zxc_seekable_open_reader.argtypes = [C.c_void_p]
+    hr = L.zxc_seekable_open_reader(C.byref(rd))
+    off, ln = 5 * bs + 1000, (70 << 20) + 3
+    out = np.zeros(ln, np.uint8)
+    assert L.zxc_seekable_decompress_range_mt(hr, out.ctypes.data, ln, off, ln, 8) == ln
+    assert np.array_equal(out, data[off:off + ln])
+    L.zxc_seekable_free(hr)

@@ -90,6 +90,34 @@ def test_mutation_parity_with_reference(prod, ref):
         assert same >= trials * 0.9, (level, same)
 
 
+def test_damaged_block_that_decodes_past_block_size(prod, ref):
+    """The reference gives each block block_size + ZXC_DECOMPRESS_TAIL_PAD of room (zxc_dispatch.c:902) and asks about
+    the caller's capacity afterwards, so this frame (one extras byte changed: block 1 grows past 64 KiB) is
+    DST_TOO_SMALL with an exact buffer and CORRUPT_DATA (footer) with a roomy one."""
+    data = zc.silesia_shaped(8 << 20, seed=33)[:300000]
+    f = ref.compress(data, level=1, block_size=65536).copy()
+    f[90026] = 76
+    for cap in (300000, 300000 + 2111, 400000):
+        r0, _ = ref.decompress(f, cap)
+        r1, _ = prod.decompress(f, cap)
+        assert r0 == r1 and r0 < 0, (cap, r0, r1)
+    assert ref.decompress(f, 300000)[0] == -2 and ref.decompress(f, 400000)[0] == -8
+    rng = np.random.default_rng(11)
+    same = trials = 0
+    for t in range(60):  # varint-area damage in general: verdicts must agree, not just their sign
+        g = ref.compress(data, level=1 + (t % 5), block_size=65536).copy()
+        for _ in range(2):
+            g[int(rng.integers(16, g.size - 12))] = int(rng.integers(0, 256))
+        r0, o0 = ref.decompress(g, 300000)
+        r1, o1 = prod.decompress(g, 300000)
+        assert (r0 < 0) == (r1 < 0), (t, r0, r1)
+        if r0 >= 0:
+            assert r0 == r1 and np.array_equal(o0, o1)
+        trials += 1
+        same += r0 == r1
+    assert same >= trials - 3, (same, trials)
+
+
 def test_capacity_semantics(prod, ref):
     data = zc.silesia_shaped(1 << 20, seed=8)[:300000]
     frame = ref.compress(data, level=3, block_size=65536, seekable=1)

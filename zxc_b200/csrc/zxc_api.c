@@ -341,9 +341,22 @@ zxc_cctx* zxc_init_static_cctx(void* workspace, const size_t workspace_size, con
 /* ------------------------------------------------------------------------- */
 /* frame decode                                                              */
 /* ------------------------------------------------------------------------- */
+/* First job in stream order that did not produce exactly its planned size.  *size_mismatch = 1 when the plan, not
+ * the block, may be at fault: a block decoded to another size, or -- block_size != 0 -- a block that was given less
+ * room than block_size (the frame's tail) ran out of it.  The reference decodes every block into block_size bytes
+ * and only then asks whether the result still fits (DST_TOO_SMALL, zxc_dispatch.c:912-1001); the caller re-plans. */
+/* The reference hands every block block_size + ZXC_DECOMPRESS_TAIL_PAD bytes of room (zxc_dispatch.c:902,
+ * :961-976) and only afterwards asks whether the result fits the caller's buffer, so a damaged block may
+ * legally decode to a little more than block_size.  The regular plan gives block i exactly its expected
+ * size; a block that ran out of room there (OVERFLOW, or DST_TOO_SMALL from the literal count) is therefore
+ * not a verdict yet but a plan mismatch, settled by the general split below. */
 static int64_t first_failure(const int32_t* st, const zxc_b200_job_t* jobs, size_t n, int* size_mismatch) {
     *size_mismatch = 0;
     for (size_t i = 0; i < n; i++) {
+        if (st[i] == ZXC_ERROR_OVERFLOW || st[i] == ZXC_ERROR_DST_TOO_SMALL) {
+            *size_mismatch = 1;
+            return st[i];
+        }
         if (st[i] < 0) return st[i];
         if ((uint32_t)st[i] != jobs[i].dst_cap) {
             *size_mismatch = 1;
@@ -373,15 +386,16 @@ static int64_t decompress_frame_any_split(zxg_ctx* g, const uint8_t* src, const 
     int rc = zxg_h2d(g, d_in, src + src_lo, (size_t)(src_hi - src_lo));
     if (rc != ZXC_OK) { ret = rc; goto out; }
     /* pass 1: sizes, a window of blocks at a time (the bytes are thrown away) */
-    const size_t win = ((size_t)256 << 20) / bs ? ((size_t)256 << 20) / bs : 1;
+    const size_t room = (size_t)bs + ZXF_TAIL_PAD; /* what the reference gives one block (:902) */
+    const size_t win = ((size_t)256 << 20) / room ? ((size_t)256 << 20) / room : 1;
     for (size_t i0 = 0; i0 < n; i0 += win) {
         const size_t cnt = n - i0 < win ? n - i0 : win;
-        uint8_t* d_tmp = (uint8_t*)zxg_buffer(g, ZXG_BUF_OUT, cnt * (size_t)bs + 16);
+        uint8_t* d_tmp = (uint8_t*)zxg_buffer(g, ZXG_BUF_OUT, cnt * room + 16);
         if (!d_tmp) { ret = ZXC_ERROR_MEMORY; goto out; }
         for (size_t k = 0; k < cnt; k++) {
             jobs[i0 + k] = w->jobs[i0 + k];
-            jobs[i0 + k].dst_off = (uint64_t)k * bs;
-            jobs[i0 + k].dst_cap = bs;
+            jobs[i0 + k].dst_off = (uint64_t)k * room;
+            jobs[i0 + k].dst_cap = (uint32_t)room;
         }
         rc = zxg_decode_jobs(g, d_in - src_lo, d_tmp, jobs + i0, (uint32_t)cnt, st + i0, dict, (uint32_t)dict_size, dict_huf, bs,
                              verify);

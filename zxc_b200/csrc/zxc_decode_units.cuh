@@ -232,8 +232,8 @@ __device__ __noinline__ int decode_lz_units(const u8* lit, u32 n_lit_avail, cons
     }
     for (;;) {
         /* the piece in front of this lane */
-        bool is_lit = false, slow = false, need = false;
-        u32 n = 0, d = 0;
+        bool is_lit = false, slow = false, need = false, fold = false;
+        u32 n = 0, d = 0, rot = 0;
         i32 s0 = 0;
         u32 ua = 0, ub = 0;
         if (active) {
@@ -247,10 +247,28 @@ __device__ __noinline__ int decode_lz_units(const u8* lit, u32 n_lit_avail, cons
             d = pos & 15u;
             if (!is_lit) {
                 s0 = (i32)pos - coff;
+                const i32 kk = (i32)pos - cmd; /* offset into the match */
+                if (kk >= coff && cmd < (i32)(u << 4) && cmd - coff >= 0) {
+                    /* the plain source lies inside this very match, written by units next door: a run longer than a
+                     * unit would make every unit wait for the one before it.  Byte-serial semantics make the match
+                     * periodic, so read the period in front of the match instead (zxc_decompress.c:197-413 does the
+                     * same with shuffle tables): position kk of the match equals position kk mod coff. */
+                    rot = z2_mod((u32)kk, (u32)coff);
+                    if (coff >= 16) {
+                        n = min(n, (u32)coff - rot); /* a piece that would wrap ends at the period boundary */
+                        s0 = cmd - coff + (i32)rot;
+                    } else {
+                        fold = out16; /* the register path below; the byte loop keeps the plain source (and its readiness) */
+                    }
+                }
                 const i32 s1 = s0 + (i32)n - 1;
                 slow = coff < 16 || (s0 < 0 && s1 >= 0);
                 /* units this piece reads: byte-serial copies reach back `coff` bytes from pos */
-                if (s1 >= 0) {
+                if (fold) {
+                    need = true;
+                    ua = (u32)(cmd - coff) >> 4;
+                    ub = (u32)(cmd - 1) >> 4;
+                } else if (s1 >= 0) {
                     need = true;
                     ua = (u32)max(s0, 0) >> 4;
                     ub = (u32)s1 >> 4;
@@ -272,18 +290,35 @@ __device__ __noinline__ int decode_lz_units(const u8* lit, u32 n_lit_avail, cons
                 a1 = (a1 & m1) | (w1 & ~m1);
                 a2 = (a2 & m2) | (w2 & ~m2);
                 a3 = (a3 & m3) | (w3 & ~m3);
-            } else if (s0 >= 0 && out16) {
+            } else if ((fold || s0 >= 0) && out16) {
                 /* distance below 16 inside the window: the piece repeats the `coff` bytes in front of it.  Take the
-                 * 16 bytes that end at pos (previous unit : own registers), keep the last `coff`, double the run
-                 * until it covers a unit, and put it behind the bytes the unit already has. */
+                 * 16 bytes that end at pos (previous unit : own registers) -- or, for a match that began before this
+                 * unit, the 16 bytes that end at the match start, rotated to this position's phase -- keep the last
+                 * `coff`, double the run until it covers a unit, and put it behind the bytes the unit already has. */
                 const u32 u0 = u << 4;
-                uint4 Pv = make_uint4(0, 0, 0, 0);
-                if (s0 < (i32)u0) Pv = *reinterpret_cast<const uint4*>(out + u0 - 16u);
                 u32 h0, h1, h2, h3;
-                uw_extract16(Pv, make_uint4(a0, a1, a2, a3), d, h0, h1, h2, h3);
+                if (fold) {
+                    uw_read16(out + cmd - 16, 16u - (u32)coff, 16u, h0, h1, h2, h3);
+                } else {
+                    uint4 Pv = make_uint4(0, 0, 0, 0);
+                    if (s0 < (i32)u0) Pv = *reinterpret_cast<const uint4*>(out + u0 - 16u);
+                    uw_extract16(Pv, make_uint4(a0, a1, a2, a3), d, h0, h1, h2, h3);
+                }
                 /* pattern = bytes 16-coff .. 15 of h, moved to the bottom (a right shift by 16-coff bytes) */
                 u32 x0, x1, x2, x3;
                 uw_extract16(make_uint4(h0, h1, h2, h3), make_uint4(0, 0, 0, 0), 16u - (u32)coff, x0, x1, x2, x3);
+                if (fold && rot) { /* rotate the period: byte i becomes byte (i + rot) mod coff */
+                    u32 p0, p1, p2, p3;
+                    uw_extract16(make_uint4(x0, x1, x2, x3), make_uint4(0, 0, 0, 0), rot, p0, p1, p2, p3);
+                    uw_shl128(x0, x1, x2, x3, (u32)coff - rot);
+                    const u32 c = (u32)coff;
+                    const u64 l64 = c >= 8u ? ~0ull : ((1ull << (8u * c)) - 1ull);
+                    const u64 g64 = c <= 8u ? 0ull : ((1ull << (8u * (c - 8u))) - 1ull);
+                    x0 = (x0 | p0) & (u32)l64;
+                    x1 = (x1 | p1) & (u32)(l64 >> 32);
+                    x2 = (x2 | p2) & (u32)g64;
+                    x3 = (x3 | p3) & (u32)(g64 >> 32);
+                }
 #pragma unroll 1
                 for (u32 len = (u32)coff; len < 16u; len <<= 1) {
                     u32 y0 = x0, y1 = x1, y2 = x2, y3 = x3;
