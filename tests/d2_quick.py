@@ -53,9 +53,18 @@ if not np.array_equal(got, data):
     print("MISMATCH bytes", w.size, "first", w[:10], "blocks", np.unique(w // bs)[:20])
     sys.exit(1)
 print("bytes identical")
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(iters): step()
-e1.record(); torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / iters
+def timed():
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters): step()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+ms = timed()
 print("ms/step %.3f  decode GB/s %.1f  (C+U) GB/s %.1f" % (ms, n / ms / 1e6, (n + frame.size) / ms / 1e6))
+for x in os.environ.get("D2_EXP_LIST", "").split(","):  # development switches (ZXC_B200_EXP), A/B in one process
+    if not x: continue
+    os.environ["ZXC_B200_EXP"] = x
+    step(); torch.cuda.synchronize()
+    ok = bool(torch.equal(d_dst, torch.from_numpy(data).to(dev)))
+    ms = min(timed(), timed())
+    print("EXP=%s: identical=%s ms/step %.3f  decode GB/s %.1f" % (x, ok, ms, n / ms / 1e6))

@@ -56,6 +56,8 @@ static pthread_mutex_t g_pool_mu = PTHREAD_MUTEX_INITIALIZER;
 #define POOL_MAX_THREADS 32
 #define POOL_SLICE ((size_t)512 << 10)
 
+extern "C" void zxh_stream_copy(void* dst, const void* src, size_t n); /* zxc_hostcopy.c */
+
 struct copy_pool {
     pthread_mutex_t job_mu; /* one job at a time */
     pthread_mutex_t mu;
@@ -130,7 +132,7 @@ static void pool_run_slices(copy_pool* p) {
         const size_t off = __atomic_fetch_add(&p->next, POOL_SLICE, __ATOMIC_RELAXED);
         if (off >= p->bytes) break;
         const size_t n = p->bytes - off < POOL_SLICE ? p->bytes - off : POOL_SLICE;
-        memcpy(p->d + off, p->s + off, n);
+        zxh_stream_copy(p->d + off, p->s + off, n);
     }
 }
 
@@ -186,7 +188,7 @@ static copy_pool* pool_copy_begin(int dev, void* dst, const void* src, size_t n)
     if (dev < 0 || dev >= POOL_MAX_DEV / 2) dev = 0;
     copy_pool* p = pool_for_device(dev + POOL_MAX_DEV / 2);
     if (p->n_threads == 0 || n < ((size_t)2 << 20)) {
-        memcpy(dst, src, n);
+        zxh_stream_copy(dst, src, n);
         return NULL;
     }
     pthread_mutex_lock(&p->job_mu);
@@ -211,7 +213,7 @@ static void pool_copy_end(copy_pool* p) {
 
 static void pool_memcpy(int dev, void* dst, const void* src, size_t n) {
     if (n < ((size_t)2 << 20)) {
-        memcpy(dst, src, n);
+        zxh_stream_copy(dst, src, n);
         return;
     }
     if (dev < 0 || dev >= POOL_MAX_DEV / 2) dev = 0;
