@@ -31,12 +31,18 @@ typedef uint64_t u64;
 typedef int32_t i32;
 
 #define FULL 0xFFFFFFFFu
+#ifndef WARPS_PER_CTA
 #define WARPS_PER_CTA 4
+#endif
 #define CTA_THREADS (WARPS_PER_CTA * 32)
+#ifndef RING_BYTES
 #define RING_BYTES 4096u          /* per-warp output ring (power of two, multiple of 512) */
+#endif
 #define RING_LIMIT (RING_BYTES - 576u) /* largest output span one batch may add */
 #define DECODE_SMEM_BYTES (WARPS_PER_CTA * RING_BYTES)
+#ifndef CTAS_PER_SM
 #define CTAS_PER_SM 7u            /* register-limited (72 regs x 128 threads); 112 KB of rings, rest is L1 */
+#endif
 
 #define BT_RAW 0
 #define BT_GLO 1
