@@ -262,3 +262,51 @@ def test_large_unaligned_ranges_through_the_pipelines(prod, ref):
     assert L.zxc_seekable_decompress_range_mt(hr, out.ctypes.data, ln, off, ln, 8) == ln
     assert np.array_equal(out, data[off:off + ln])
     L.zxc_seekable_free(hr)
+
+
+def test_one_call_over_several_devices(prod, ref):
+    """ZXC_B200_DEVICES: one zxc_decompress / zxc_seekable_decompress_range_mt call fans its block stripes out over
+    the visible devices (zxc_api.c decode_multi), the reference's fork-join (zxc_seekable.c:999-1108) with devices for
+    threads.  Same bytes, same verdicts as the single-device route."""
+    import os
+    import torch
+    if prod.lib.zxc_b200_device_count() < 2:
+        pytest.skip("needs two devices")
+    data = zc.silesia_shaped(400 << 20, seed=12)
+    bs = 65536
+    frame = zc.compress_ref_mt(ref, data, level=3, block_size=bs, checksum=1)
+    L = prod.lib
+    os.environ["ZXC_B200_DEVICES"] = "all"
+    try:
+        n0 = L.zxc_b200_launch_count()
+        r, out = prod.decompress(frame, data.size, checksum=1)  # pageable: staged stripes
+        assert r == data.size and np.array_equal(out, data)
+        assert L.zxc_b200_launch_count() - n0 >= 2
+        h_frame = torch.from_numpy(frame).pin_memory()  # page-locked: direct stripes
+        h_out = torch.zeros(data.size, dtype=torch.uint8).pin_memory()
+        o = z.DecompressOpts(checksum_enabled=1)
+        assert L.zxc_decompress(h_frame.data_ptr(), h_frame.numel(), h_out.data_ptr(), data.size, C.byref(o)) == data.size
+        assert np.array_equal(h_out.numpy(), data)
+        f2 = frame.copy()  # damage in the last stripe: the reference's code
+        f2[int(f2.size * 0.93)] ^= 0x21
+        r0, _ = ref.decompress(f2, data.size, checksum=1)
+        r1, _ = prod.decompress(f2, data.size, checksum=1)
+        assert r0 == r1 < 0, (r0, r1)
+        h = L.zxc_seekable_open(frame.ctypes.data, frame.size)
+        for off, ln in ((3, data.size - 5), (7 * bs + 11, (300 << 20) + 1)):
+            rout = np.zeros(ln, np.uint8)
+            assert L.zxc_seekable_decompress_range_mt(h, rout.ctypes.data, ln, off, ln, 8) == ln
+            assert np.array_equal(rout, data[off:off + ln]), (off, ln)
+        L.zxc_seekable_free(h)
+        calls = []
+        rd, keep = make_reader(frame, calls)  # reader-backed: read_at called from every stripe's thread
+        L.zxc_seekable_open_reader.restype = C.c_void_p
+        L.zxc_seekable_open_reader.argtypes = [C.c_void_p]
+        hr = L.zxc_seekable_open_reader(C.byref(rd))
+        off, ln = 2 * bs + 5, (350 << 20) + 9
+        rout = np.zeros(ln, np.uint8)
+        assert L.zxc_seekable_decompress_range_mt(hr, rout.ctypes.data, ln, off, ln, 8) == ln
+        assert np.array_equal(rout, data[off:off + ln])
+        L.zxc_seekable_free(hr)
+    finally:
+        del os.environ["ZXC_B200_DEVICES"]

@@ -16,9 +16,12 @@
  *   dict id / .zxd                   zxc_dict.c:35-205
  *   bounds, names                    zxc_common.c:850-1017
  */
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/types.h>
+#include <unistd.h>
 
 #include "zxc.h"
 #include "zxc_b200.h"
@@ -345,6 +348,122 @@ zxc_cctx* zxc_init_static_cctx(void* workspace, const size_t workspace_size, con
  * the block, may be at fault: a block decoded to another size, or -- block_size != 0 -- a block that was given less
  * room than block_size (the frame's tail) ran out of it.  The reference decodes every block into block_size bytes
  * and only then asks whether the result still fits (DST_TOO_SMALL, zxc_dispatch.c:912-1001); the caller re-plans. */
+/* ---- several GPUs behind one call -------------------------------------------------------------------------
+ * The reference's data-parallel entry is a fork-join over host threads (zxc_seekable.c:999-1108: contiguous block
+ * stripes, one worker each).  The same split works over devices: with ZXC_B200_DEVICES=<n> | all in the environment
+ * (opt-in; default 1) a large frame or range is cut into contiguous block stripes, one host thread per device runs
+ * the usual overlapped H2D / decode / D2H pipeline on its stripe through a context of that device (its own PCIe
+ * link, copy pool and NUMA-local bounce buffers), and the statuses land in one table so the verdict logic is the
+ * single-device one.  Never on by default: a process launched once per GPU (torchrun) must not fan out again. */
+#define ZX_MAX_DEV 16
+typedef struct {
+    int device, own_thread;
+    zxg_ctx* g;
+    const uint8_t* src;
+    zxg_fetch_fn fetch;
+    void* fetch_ctx;
+    uint8_t* dst;              /* where decoded byte clip_lo lands */
+    uint64_t clip_lo, clip_hi; /* decoded range wanted, job coordinates */
+    const zxc_b200_job_t* jobs;
+    uint32_t n;
+    int32_t* st;
+    const void* dict;
+    uint32_t dict_size;
+    const void* dict_huf;
+    uint32_t bs;
+    int verify, pinned, rc;
+} zx_part;
+
+static void part_run(zx_part* p, zxg_ctx* g) {
+    const uint32_t n = p->n;
+    zxc_b200_job_t* jb = (zxc_b200_job_t*)malloc((size_t)n * sizeof *jb);
+    if (!jb) { p->rc = ZXC_ERROR_MEMORY; return; }
+    const uint64_t d0 = p->jobs[0].dst_off, d1 = p->jobs[n - 1].dst_off + p->jobs[n - 1].dst_cap;
+    for (uint32_t i = 0; i < n; i++) {
+        jb[i] = p->jobs[i];
+        jb[i].dst_off -= d0; /* stripe-local decoded coordinates; source offsets stay absolute */
+    }
+    const uint64_t src_lo = p->jobs[0].src_off, src_hi = p->jobs[n - 1].src_off + p->jobs[n - 1].src_len;
+    const uint64_t lo = p->clip_lo > d0 ? p->clip_lo : d0, hi = p->clip_hi < d1 ? p->clip_hi : d1;
+    uint8_t* out = p->dst + (lo - p->clip_lo);
+    if (p->pinned && !p->fetch && lo == d0 && hi == d1)
+        p->rc = zxg_decode_pipelined(g, p->src, src_lo, src_hi, out, d1 - d0, jb, n, p->st, p->dict, p->dict_size,
+                                     p->dict_huf, p->bs, p->verify);
+    else
+        p->rc = zxg_decode_staged(g, p->src, p->fetch, p->fetch_ctx, src_lo, src_hi, out, lo - d0, hi - d0, jb, n, p->st,
+                                  p->dict, p->dict_size, p->dict_huf, p->bs, p->verify);
+    free(jb);
+}
+
+static void* part_main(void* arg) {
+    zx_part* p = (zx_part*)arg;
+    p->rc = zxg_set_device(p->device);
+    if (p->rc != ZXC_OK) return NULL;
+    zxg_ctx* g = zxg_acquire();
+    if (!g) { p->rc = ZXC_ERROR_MEMORY; return NULL; }
+    part_run(p, g);
+    zxg_release(g);
+    return NULL;
+}
+
+/* how many devices a call decoding `decoded_bytes` may use: the environment's wish, the devices there are, and at
+ * least 64 MiB of output per stripe */
+static int multi_devices(uint64_t decoded_bytes) {
+    const char* e = getenv("ZXC_B200_DEVICES");
+    if (!e || !*e) return 1;
+    int want = strcmp(e, "all") == 0 ? ZX_MAX_DEV : atoi(e);
+    if (want <= 1) return 1;
+    const int nd = zxg_device_count();
+    if (want > nd) want = nd;
+    if (want > ZX_MAX_DEV) want = ZX_MAX_DEV;
+    const uint64_t by_size = decoded_bytes >> 26;
+    if ((uint64_t)want > by_size) want = (int)by_size;
+    return want < 1 ? 1 : want;
+}
+
+/* jobs (contiguous, dst_off ascending) over D devices; g0 = the caller's context (stripe 0, calling thread) */
+static int decode_multi(int D, zxg_ctx* g0, const uint8_t* src, zxg_fetch_fn fetch, void* fetch_ctx, uint8_t* dst,
+                        uint64_t clip_lo, uint64_t clip_hi, const zxc_b200_job_t* jobs, uint32_t n, int32_t* st,
+                        const void* dict, uint32_t dict_size, const void* dict_huf, uint32_t bs, int verify, int pinned) {
+    zx_part parts[ZX_MAX_DEV];
+    pthread_t th[ZX_MAX_DEV];
+    const int cur = zxg_current_device(), nd = zxg_device_count();
+    const uint32_t per = (n + (uint32_t)D - 1) / (uint32_t)D;
+    int np = 0;
+    for (uint32_t start = 0; start < n && np < ZX_MAX_DEV; start += per, np++) {
+        zx_part* p = &parts[np];
+        memset(p, 0, sizeof *p);
+        p->device = (cur + np) % (nd > 0 ? nd : 1);
+        p->src = src;
+        p->fetch = fetch;
+        p->fetch_ctx = fetch_ctx;
+        p->dst = dst;
+        p->clip_lo = clip_lo;
+        p->clip_hi = clip_hi;
+        p->jobs = jobs + start;
+        p->n = n - start < per ? n - start : per;
+        p->st = st + start;
+        p->dict = dict;
+        p->dict_size = dict_size;
+        p->dict_huf = dict_huf;
+        p->bs = bs;
+        p->verify = verify;
+        p->pinned = pinned;
+    }
+    for (int k = 1; k < np; k++) parts[k].own_thread = pthread_create(&th[k], NULL, part_main, &parts[k]) == 0;
+    part_run(&parts[0], g0);
+    for (int k = 1; k < np; k++) {
+        if (parts[k].own_thread) pthread_join(th[k], NULL);
+        else { /* no thread to be had: this stripe on the caller's device after all */
+            part_run(&parts[k], g0);
+        }
+    }
+    zxg_set_device(cur);
+    for (int k = 0; k < np; k++)
+        if (parts[k].rc != ZXC_OK) return parts[k].rc;
+    return ZXC_OK;
+}
+
 /* The reference hands every block block_size + ZXC_DECOMPRESS_TAIL_PAD bytes of room (zxc_dispatch.c:902,
  * :961-976) and only afterwards asks whether the result fits the caller's buffer, so a damaged block may
  * legally decode to a little more than block_size.  The regular plan gives block i exactly its expected
@@ -470,8 +589,11 @@ static int64_t decompress_frame(zxg_ctx* g, const uint8_t* src, size_t src_size,
         const int overlap = (const uint8_t*)src < dst + dst_capacity && dst < (const uint8_t*)src + src_size;
         if (!overlap && produced >= ((uint64_t)32 << 20) && zxg_host_pinned(src) && zxg_host_pinned(dst)) {
             /* page-locked caller buffers: overlap H2D, decode and D2H chunk by chunk */
-            const int prc = zxg_decode_pipelined(g, src, src_lo, src_hi, dst, produced, w.jobs, (uint32_t)n_fit, status,
-                                                 dict, (uint32_t)dict_size, dict_huf, w.block_size, verify);
+            const int D = multi_devices(produced);
+            const int prc = D > 1 ? decode_multi(D, g, src, NULL, NULL, dst, 0, produced, w.jobs, (uint32_t)n_fit, status, dict,
+                                                 (uint32_t)dict_size, dict_huf, w.block_size, verify, 1)
+                                  : zxg_decode_pipelined(g, src, src_lo, src_hi, dst, produced, w.jobs, (uint32_t)n_fit, status,
+                                                         dict, (uint32_t)dict_size, dict_huf, w.block_size, verify);
             if (prc != ZXC_OK) { ret = prc; goto out; }
             int mm = 0;
             const int64_t pf = first_failure(status, w.jobs, n_fit, &mm);
@@ -481,8 +603,11 @@ static int64_t decompress_frame(zxg_ctx* g, const uint8_t* src, size_t src_size,
         }
         if (!overlap && produced >= ((uint64_t)32 << 20)) {
             /* ordinary (pageable) caller memory: the same overlap through pinned bounce buffers and the copy pool */
-            const int prc = zxg_decode_staged(g, src, NULL, NULL, src_lo, src_hi, dst, 0, produced, w.jobs, (uint32_t)n_fit,
-                                              status, dict, (uint32_t)dict_size, dict_huf, w.block_size, verify);
+            const int D = multi_devices(produced);
+            const int prc = D > 1 ? decode_multi(D, g, src, NULL, NULL, dst, 0, produced, w.jobs, (uint32_t)n_fit, status, dict,
+                                                 (uint32_t)dict_size, dict_huf, w.block_size, verify, 0)
+                                  : zxg_decode_staged(g, src, NULL, NULL, src_lo, src_hi, dst, 0, produced, w.jobs, (uint32_t)n_fit,
+                                                      status, dict, (uint32_t)dict_size, dict_huf, w.block_size, verify);
             if (prc != ZXC_OK) { ret = prc; goto out; }
             int mm = 0;
             const int64_t pf = first_failure(status, w.jobs, n_fit, &mm);
@@ -904,7 +1029,12 @@ static int64_t seekable_range(zxc_seekable* s, void* dst, size_t dst_capacity, u
         for (uint32_t i = 0; i < nb; i++) jobs[i].src_off += c_lo;
         const uint64_t clip_lo = offset - out_lo, clip_hi = clip_lo + len;
         const int aligned = clip_lo == 0 && clip_hi == out_bytes;
-        if (s->src && aligned && zxg_host_pinned(s->src) && zxg_host_pinned(dst))
+        const int D = multi_devices(out_bytes);
+        if (D > 1)
+            rc = decode_multi(D, g, s->src, s->src ? NULL : seekable_fetch, s, (uint8_t*)dst, clip_lo, clip_hi, jobs, nb, st,
+                              s->dict, (uint32_t)s->dict_size, s->has_dict_huf ? s->dict_huf : NULL, bs, 0,
+                              s->src && zxg_host_pinned(s->src) && zxg_host_pinned(dst));
+        else if (s->src && aligned && zxg_host_pinned(s->src) && zxg_host_pinned(dst))
             rc = zxg_decode_pipelined(g, s->src, c_lo, c_hi, (uint8_t*)dst, out_bytes, jobs, nb, st, s->dict,
                                       (uint32_t)s->dict_size, s->has_dict_huf ? s->dict_huf : NULL, bs, 0);
         else
@@ -1042,10 +1172,27 @@ int64_t zxc_stream_get_decompressed_size(FILE* f_in) {
     return r;
 }
 
+/* positioned reads like the reference's FILE* reader (zxc_seekable.c:414-421: pread, safe from several threads); a
+ * stream without a descriptor (fmemopen) falls back to fseek + fread under a lock */
+static pthread_mutex_t g_file_mu = PTHREAD_MUTEX_INITIALIZER;
 static int64_t file_read_at(void* ctx, void* dst, size_t len, uint64_t offset) {
     FILE* f = (FILE*)((void**)ctx)[0];
-    if (fseek(f, (long)offset, SEEK_SET) != 0) return ZXC_ERROR_IO;
-    return (int64_t)fread(dst, 1, len, f);
+    const int fd = fileno(f);
+    if (fd >= 0) {
+        size_t got = 0;
+        while (got < len) {
+            const ssize_t r = pread(fd, (uint8_t*)dst + got, len - got, (off_t)(offset + got));
+            if (r < 0) return ZXC_ERROR_IO;
+            if (r == 0) break;
+            got += (size_t)r;
+        }
+        return (int64_t)got;
+    }
+    pthread_mutex_lock(&g_file_mu);
+    int64_t r = ZXC_ERROR_IO;
+    if (fseek(f, (long)offset, SEEK_SET) == 0) r = (int64_t)fread(dst, 1, len, f);
+    pthread_mutex_unlock(&g_file_mu);
+    return r;
 }
 
 zxc_seekable* zxc_seekable_open_file(FILE* f) {

@@ -336,6 +336,23 @@ extern "C" int zxc_b200_device_count(void) {
 
 extern "C" uint64_t zxc_b200_launch_count(void) { return g_launches; }
 
+extern "C" int zxg_current_device(void) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return dev;
+}
+extern "C" int zxg_device_count(void) { return zxc_b200_device_count(); }
+extern "C" int zxg_set_device(int dev) {
+    if (cudaSetDevice(dev) != cudaSuccess) {
+        cudaGetLastError();
+        return ZXC_B200_ERROR_CUDA;
+    }
+    return ZXC_OK;
+}
+
 extern "C" zxg_ctx* zxg_create(void) {
     if (zxg_init() != ZXC_OK) return NULL;
     zxg_ctx* c = (zxg_ctx*)calloc(1, sizeof(zxg_ctx));

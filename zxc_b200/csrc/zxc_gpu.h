@@ -51,6 +51,12 @@ int zxg_encode_body(zxg_ctx* c, const uint8_t* h_src, uint64_t src_size, uint32_
                     int checksum, uint32_t n_blocks, uint8_t* h_body, uint64_t body_cap, uint32_t* h_sizes,
                     uint64_t* body_size, const void* h_dict, uint32_t dict_size, const uint8_t* h_dict_huf_lens);
 
+/* Device selection for the calling thread (multi-device fork-join in zxc_api.c): current device, device count,
+ * cudaSetDevice.  zxg_acquire() hands out a context of the calling thread's current device. */
+int zxg_current_device(void);
+int zxg_device_count(void);
+int zxg_set_device(int dev); /* ZXC_OK or ZXC_B200_ERROR_CUDA */
+
 /* 1 when the pointer is page-locked (cudaHostAlloc / cudaHostRegister / managed) */
 int zxg_host_pinned(const void* p);
 
