@@ -602,6 +602,54 @@ def main():
         dist.all_reduce(t_p, op=dist.ReduceOp.MAX)
     e2e_pageable = (n * world) / float(t_p.item()) / 1e9
 
+    # ---- supplementary (N > 1): ONE zxc_decompress call on rank 0 fanned out over all N devices by the library itself
+    # (ZXC_B200_DEVICES, zxc_api.c decode_multi) -- what a single-process caller of the drop-in gets from the box;
+    # the other ranks idle at the barrier meanwhile
+    one_call = None
+    if world > 1:
+        # the waiting ranks poll a flag file instead of sitting in an NCCL barrier kernel on the GPUs rank 0 is using
+        flag = "/tmp/zxc_bench_one_call_%s.done" % os.environ.get("MASTER_PORT", "0")
+        if rank == 0 and os.path.exists(flag):
+            os.unlink(flag)
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        if rank == 0:
+            mine = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, all_cpus)  # the stripes' copy pools bind themselves to their own device's node
+            os.environ["ZXC_B200_DEVICES"] = str(world)
+            try:
+                h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
+                p_out = np.zeros(n, dtype=np.uint8)
+                rates = {}
+                for name, src_p, src_n, dst_p in (("page_locked", h_frame.data_ptr(), h_frame.numel(), h_out.data_ptr()),
+                                                  ("pageable", frame.ctypes.data, frame.size, p_out.ctypes.data)):
+                    for _ in range(2):
+                        r = prod.lib.zxc_decompress(src_p, src_n, dst_p, n, None)
+                        assert r == n, r
+                    t0 = time.perf_counter()
+                    for _ in range(3):
+                        r = prod.lib.zxc_decompress(src_p, src_n, dst_p, n, None)
+                    rates[name] = n / ((time.perf_counter() - t0) / 3) / 1e9
+                    assert r == n
+                if not args.no_verify:
+                    assert np.array_equal(h_out.numpy(), data) and np.array_equal(p_out, data), "one-call output differs"
+                one_call = {"devices": world, "decoded_bytes": int(n), "unit": "GB/s",
+                            "page_locked": round(rates["page_locked"], 2), "pageable": round(rates["pageable"], 2),
+                            "api": "one zxc_decompress(host frame, host dst) call on rank 0, ZXC_B200_DEVICES=%d: block stripes "
+                                   "fork-joined over the devices inside the library" % world}
+                del h_out, p_out
+            finally:
+                del os.environ["ZXC_B200_DEVICES"]
+                os.sched_setaffinity(0, mine)
+                open(flag, "w").close()
+        else:
+            t_wait = time.perf_counter()
+            while not os.path.exists(flag) and time.perf_counter() - t_wait < 600:
+                time.sleep(0.05)
+        dist.barrier()
+        if rank == 0:
+            os.unlink(flag)
+
     # ---- supplementary: NVLink gather of decoded output (N > 1), bounded slice
     gather = None
     if world > 1:
@@ -655,6 +703,8 @@ def main():
             line["gather"] = gather
         if pipeline:
             line["pipeline"] = pipeline
+        if one_call:
+            line["e2e_one_call"] = one_call
         line["numa"] = numa
         if world == 1 and not args.decode_only:
             os.sched_setaffinity(0, all_cpus)  # the CPU baseline may use every host core again
