@@ -298,6 +298,7 @@ struct zxg_ctx {
     int device;
     int numa_node;
     int sm_count;
+    int trimmed; /* idle and already cut back by zxg_release */
 };
 static zxg_ctx* g_free_list = NULL;
 
@@ -415,11 +416,41 @@ extern "C" zxg_ctx* zxg_acquire(void) {
     return zxg_create();
 }
 
+/* Gives back what an idle context holds beyond `keep` bytes per buffer (and its staging slots). */
+static void ctx_trim(zxg_ctx* c, size_t keep) {
+    cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < ZXG_BUF_COUNT; i++)
+        if (c->buf[i] && c->cap[i] > keep) {
+            cudaFree(c->buf[i]);
+            c->buf[i] = NULL;
+            c->cap[i] = 0;
+        }
+    for (int i = 0; i < STAGE_SLOTS; i++) {
+        pinned_free(&c->st_in[i]);
+        pinned_free(&c->st_out[i]);
+    }
+}
+
+/* The free list keeps contexts warm: the two most recently released contexts of a device keep their buffers (a
+ * caller that decodes frame after frame should not pay cudaMalloc each time); older idle ones -- left behind by a
+ * burst of concurrent callers -- are trimmed to POOL_KEEP_BYTES per buffer so that one multi-GiB frame does not pin
+ * several GiB of HBM per past thread for the life of the process. */
+#define POOL_WARM_PER_DEVICE 2
+#define POOL_KEEP_BYTES ((size_t)64 << 20)
 extern "C" void zxg_release(zxg_ctx* c) {
     if (!c) return;
     pthread_mutex_lock(&g_pool_mu);
     c->next = g_free_list;
     g_free_list = c;
+    int seen = 0;
+    for (zxg_ctx* q = g_free_list; q; q = q->next) {
+        if (q->device != c->device) continue;
+        if (++seen > POOL_WARM_PER_DEVICE && !q->trimmed) {
+            ctx_trim(q, POOL_KEEP_BYTES);
+            q->trimmed = 1;
+        }
+    }
+    c->trimmed = 0;
     pthread_mutex_unlock(&g_pool_mu);
 }
 
