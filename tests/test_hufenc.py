@@ -139,3 +139,28 @@ def test_randomised_histograms_match_reference(libs):
             adopted += rb
             assert h.zxhh_calc_size(f.ctypes.data, a.ctypes.data, 1) == r.zxri_calc_size(f.ctypes.data, b.ctypes.data, 1)
     assert adopted > 100
+
+
+def test_package_merge_wide_sweep(libs):
+    """The prefix-count package-merge (zxc_hufenc.h) against the reference's item-tree one: 4000 histograms biased
+    towards equal weights (where the leaf-before-package rule decides), every cap the encoder uses."""
+    h, r = libs
+    rng = np.random.default_rng(2024)
+    for t in range(4000):
+        n_sym = int(rng.integers(2, 257)) if t % 5 else int(rng.integers(2, 12))
+        f = np.zeros(256, np.uint32)
+        syms = rng.choice(256, n_sym, replace=False)
+        kind = t % 4
+        if kind == 0:
+            f[syms] = rng.integers(1, 3, n_sym)                      # almost everything ties
+        elif kind == 1:
+            f[syms] = (1 << rng.integers(0, 12, n_sym)).astype(np.uint32)  # package sums collide with leaf weights
+        elif kind == 2:
+            f[syms] = rng.integers(1, 40, n_sym)
+        else:
+            f[syms] = (rng.pareto(1.2, n_sym) * 20 + 1).clip(1, 1_000_000).astype(np.uint32)
+        for cap in (8, 9, 10, 11):
+            a, b = np.zeros(256, np.uint8), np.zeros(256, np.uint8)
+            ra = h.zxhh_build_code_lengths(f.ctypes.data, a.ctypes.data, cap)
+            rb = r.zxri_build_code_lengths(f.ctypes.data, b.ctypes.data, cap)
+            assert ra == rb and np.array_equal(a, b), (t, cap, n_sym, kind)

@@ -40,12 +40,10 @@
 #define ZXH_DP_M 64        /* most groups the nudge DP ever sees: ceil(256 / 4) */
 
 typedef struct { uint32_t w; int16_t sym; } zxh_leaf_t;
-typedef struct { uint32_t weight; int16_t left, right, sym; } zxh_item_t;
-typedef struct { int8_t lvl; int16_t idx; } zxh_frame_t;
 
 typedef struct {
-    zxh_item_t items[ZXH_LU][2 * ZXH_NSYM];
-    zxh_frame_t stack[ZXH_LU * 2 * ZXH_NSYM];
+    uint32_t pm_weight[2][2 * ZXH_NSYM];        /* package-merge: item weights of the previous / current level */
+    uint8_t pm_is_leaf[ZXH_LU][2 * ZXH_NSYM];   /* package-merge: 1 = leaf, 0 = package, per level and item */
     zxh_leaf_t leaves[ZXH_NSYM];
     zxh_leaf_t sort_tmp[ZXH_NSYM];
     uint64_t dp_a[(ZXH_DP_M + 1) * (ZXH_DP_M + 1)];
@@ -82,7 +80,19 @@ ZXH void zxh_sort_leaves(zxh_leaf_t* a, int n) {
     }
 }
 
-/* length-limited Huffman code lengths by package-merge; 0 on success */
+/* Length-limited Huffman code lengths by package-merge (same result as zxc_huf_build_code_lengths,
+ * zxc_huffman.c:172-311, for every histogram and cap -- pinned by tests/test_hufenc.py), expressed without item
+ * trees:
+ *
+ *   Level 0 is the sorted leaf list.  Level k is the merge, by weight, of the leaf list with the packages of level
+ *   k-1 (item pairs 2p, 2p+1; a leaf goes first on equal weight).  Both inputs appear in the merge in their own
+ *   order, so whatever prefix of a level is "taken" consists of a prefix of the leaves and a prefix of the packages,
+ *   and taking p packages means taking the first 2p items of the level below.  The selection is therefore one
+ *   number per level: m_top = min(2n-2, |top level|), then a_k = leaves among the first m_k items, m_(k-1) =
+ *   2 (m_k - a_k); and a symbol's code length is the number of levels whose a_k covers its rank.
+ *
+ * Forward pass: item weights of the previous level only (two rolling rows) and one leaf/package flag per item.
+ * Backward pass: L prefix counts.  No links, no traversal stack. */
 ZXH int zxh_build_code_lengths(const uint32_t* freq, uint8_t* code_len, int max_code_len, zxh_work_t* W) {
     for (int i = 0; i < ZXH_NSYM; i++) code_len[i] = 0;
     zxh_leaf_t* leaves = W->leaves;
@@ -100,56 +110,50 @@ ZXH int zxh_build_code_lengths(const uint32_t* freq, uint8_t* code_len, int max_
         return 0;
     }
     zxh_sort_leaves(leaves, n);
-    int counts[ZXH_LU];
+    int size[ZXH_LU]; /* items per level */
+    uint32_t* prev = W->pm_weight[0];
+    uint32_t* cur = W->pm_weight[1];
     for (int i = 0; i < n; i++) {
-        zxh_item_t* it = &W->items[0][i];
-        it->weight = leaves[i].w;
-        it->left = it->right = -1;
-        it->sym = leaves[i].sym;
+        prev[i] = leaves[i].w;
+        W->pm_is_leaf[0][i] = 1;
     }
-    counts[0] = n;
+    size[0] = n;
     for (int k = 1; k < max_code_len; k++) {
-        const int packs = counts[k - 1] / 2;
-        int li = 0, pi = 0, out = 0;
-        while (li < n || pi < packs) {
-            const uint32_t wl = li < n ? leaves[li].w : 0xFFFFFFFFu;
-            const uint32_t wp = pi < packs ? W->items[k - 1][2 * pi].weight + W->items[k - 1][2 * pi + 1].weight : 0xFFFFFFFFu;
-            zxh_item_t* it = &W->items[k][out++];
-            if (wl <= wp && li < n) { /* ties go to the leaf */
-                it->weight = wl;
-                it->left = it->right = -1;
-                it->sym = leaves[li++].sym;
+        const int n_pack = size[k - 1] >> 1;
+        uint8_t* flag = W->pm_is_leaf[k];
+        int leaf = 0, pack = 0, out = 0;
+        while (leaf < n && pack < n_pack) {
+            const uint32_t pw = prev[2 * pack] + prev[2 * pack + 1];
+            if (leaves[leaf].w <= pw) { /* equal weight: the leaf first */
+                cur[out] = leaves[leaf++].w;
+                flag[out++] = 1;
             } else {
-                it->weight = wp;
-                it->left = (int16_t)(2 * pi);
-                it->right = (int16_t)(2 * pi + 1);
-                it->sym = -1;
-                pi++;
+                cur[out] = pw;
+                flag[out++] = 0;
+                pack++;
             }
         }
-        counts[k] = out;
-    }
-    int take = 2 * n - 2;
-    if (take > counts[max_code_len - 1]) take = counts[max_code_len - 1];
-    int sp = 0;
-    for (int i = 0; i < take; i++) {
-        W->stack[sp].lvl = (int8_t)(max_code_len - 1);
-        W->stack[sp].idx = (int16_t)i;
-        sp++;
-    }
-    while (sp > 0) {
-        const zxh_frame_t f = W->stack[--sp];
-        const zxh_item_t* it = &W->items[f.lvl][f.idx];
-        if (it->sym >= 0) {
-            code_len[it->sym]++;
-        } else {
-            W->stack[sp].lvl = (int8_t)(f.lvl - 1);
-            W->stack[sp].idx = it->left;
-            sp++;
-            W->stack[sp].lvl = (int8_t)(f.lvl - 1);
-            W->stack[sp].idx = it->right;
-            sp++;
+        for (; leaf < n; leaf++) {
+            cur[out] = leaves[leaf].w;
+            flag[out++] = 1;
         }
+        for (; pack < n_pack; pack++) {
+            cur[out] = prev[2 * pack] + prev[2 * pack + 1];
+            flag[out++] = 0;
+        }
+        size[k] = out;
+        uint32_t* t = prev;
+        prev = cur;
+        cur = t;
+    }
+    int m = 2 * n - 2;
+    if (m > size[max_code_len - 1]) m = size[max_code_len - 1];
+    for (int k = max_code_len - 1; k >= 0 && m > 0; k--) {
+        const uint8_t* flag = W->pm_is_leaf[k];
+        int a = 0;
+        for (int i = 0; i < m; i++) a += flag[i];
+        for (int j = 0; j < a; j++) code_len[leaves[j].sym]++;
+        m = 2 * (m - a);
     }
     return 0;
 }
