@@ -208,3 +208,92 @@ def test_no_device_fails_loudly(prod):
     assert prod.lib.zxc_b200_device_count() == 0
     for level in (1, 3, 6, 7):  # every level encodes on the GPU only
         assert prod.compress(np.frombuffer(b"abcdefgh" * 64, np.uint8), level=level) == -100
+
+
+def test_host_parsers_fuzz_against_reference(prod, ref):
+    """Frame-level parsing needs no device: damaged / truncated / extended seekable frames through
+    zxc_seekable_open (+ the per-block queries), zxc_get_decompressed_size and zxc_get_dict_id give what the
+    reference gives (zxc_seekable.c:270-396, zxc_dispatch.c:1010-1075).  Damage is aimed at the regions the host
+    reads: file header, block headers, SEK block, EOF block, footer."""
+    data = zc.silesia_shaped(1 << 20, seed=9)[:400000]
+    rng = np.random.default_rng(41)
+    for L in (prod.lib, ref.lib):
+        L.zxc_seekable_open.restype = C.c_void_p
+        L.zxc_seekable_open.argtypes = [C.c_void_p, C.c_size_t]
+        L.zxc_seekable_free.argtypes = [C.c_void_p]
+        for fn in ("zxc_seekable_get_num_blocks", "zxc_seekable_get_block_comp_size", "zxc_seekable_get_block_decomp_size"):
+            getattr(L, fn).restype = C.c_uint32
+        L.zxc_seekable_get_num_blocks.argtypes = [C.c_void_p]
+        L.zxc_seekable_get_block_comp_size.argtypes = [C.c_void_p, C.c_uint32]
+        L.zxc_seekable_get_block_decomp_size.argtypes = [C.c_void_p, C.c_uint32]
+        L.zxc_seekable_get_decompressed_size.restype = C.c_uint64
+        L.zxc_seekable_get_decompressed_size.argtypes = [C.c_void_p]
+
+    def view(L, buf):
+        p, n = buf.ctypes.data, buf.size
+        out = [int(L.zxc_get_decompressed_size(p, n)), int(L.zxc_get_dict_id(p, n))]
+        h = L.zxc_seekable_open(p, n)
+        out.append(bool(h))
+        if h:
+            nb = L.zxc_seekable_get_num_blocks(h)
+            out += [nb, int(L.zxc_seekable_get_decompressed_size(h))]
+            out += [(L.zxc_seekable_get_block_comp_size(h, i), L.zxc_seekable_get_block_decomp_size(h, i)) for i in range(min(nb, 40) + 1)]
+            L.zxc_seekable_free(h)
+        return out
+
+    opened = 0
+    for bs, cks in ((4096, 0), (16384, 1), (65536, 0)):
+        frame = ref.compress(data, level=3, block_size=bs, checksum=cks, seekable=1)
+        nb = -(-data.size // bs)
+        tail = 8 + 4 * nb + 8 + 12 + 64  # SEK block + EOF block + footer and a little of the last data block
+        for t in range(220):
+            f = frame.copy()
+            kind = t % 5
+            if kind == 0:    # file header
+                f[int(rng.integers(0, 16))] = int(rng.integers(0, 256))
+            elif kind == 1:  # SEK / EOF / footer region
+                for _ in range(int(rng.integers(1, 3))):
+                    f[f.size - 1 - int(rng.integers(0, tail))] ^= int(rng.integers(1, 256))
+            elif kind == 2:  # truncated
+                f = f[:f.size - int(rng.integers(1, tail + 200))].copy()
+            elif kind == 3:  # trailing garbage
+                f = np.concatenate([f, rng.integers(0, 256, int(rng.integers(1, 40)), dtype=np.uint8)])
+            else:            # a block header somewhere in the body
+                f[16 + int(rng.integers(0, 8))] ^= int(rng.integers(1, 256))
+            a, b = view(prod.lib, f), view(ref.lib, f)
+            assert a == b, (bs, cks, t, kind, a[:5], b[:5])
+            opened += a[2]
+    assert opened > 20  # some damage leaves a frame the SEK parser still accepts: those were compared in full
+
+
+def test_dict_container_fuzz_against_reference(prod, ref):
+    """Damaged / truncated .zxd containers: zxc_dict_load and zxc_dict_get_id agree with the reference
+    (zxc_dict.c container checks: magic, version, sizes, table validity, checksum)."""
+    rng = np.random.default_rng(5)
+    for L in (prod.lib, ref.lib):
+        L.zxc_dict_save.restype = C.c_int64
+        L.zxc_dict_save.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.zxc_dict_get_id.restype = C.c_uint32
+    same_ok = 0
+    for n in (1, 40, 700, 9000):
+        d = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        for huf in (bytes([0x88] * 128), rng.integers(0, 12, 128, dtype=np.uint8).tobytes()):  # a flat table / arbitrary nibbles
+            box = np.zeros(n + 200, np.uint8)
+            sz = ref.lib.zxc_dict_save(d, n, huf, box.ctypes.data, box.size)
+            assert sz > 0
+            good = box[:sz].copy()
+            for t in range(120):
+                b = good.copy()
+                k = t % 3
+                if k == 0:
+                    b[int(rng.integers(0, min(b.size, 160)))] ^= int(rng.integers(1, 256))
+                elif k == 1:
+                    b[int(rng.integers(0, b.size))] = int(rng.integers(0, 256))
+                else:
+                    b = b[:int(rng.integers(0, b.size))].copy()
+                raw = b.tobytes()
+                a, r = prod.dict_load(raw), ref.dict_load(raw)
+                assert a == r, (n, t, a[0], r[0])
+                assert prod.lib.zxc_dict_get_id(raw, len(raw)) == ref.lib.zxc_dict_get_id(raw, len(raw))
+                same_ok += a[0] == 0
+    assert same_ok > 0
