@@ -148,6 +148,38 @@ def test_seek_table_and_plan(prod, ref, orc):
         assert bool(prod.lib.zxc_seekable_open(bad, len(bad))) == bool(ref.lib.zxc_seekable_open(bad, len(bad)))
 
 
+def test_walk_ignores_what_a_forged_seek_table_says(prod, ref):
+    """zxw_walk uses a seek table at the tail only to prefetch block headers ahead of the sequential walk
+    (zxc_frame.c); the plan must not depend on the entries: forged ones (zero, huge, random) give the same job table."""
+    class Job(C.Structure):
+        _fields_ = [("src_off", C.c_uint64), ("dst_off", C.c_uint64), ("src_len", C.c_uint32), ("dst_cap", C.c_uint32)]
+    prod.lib.zxc_b200_plan_frame.restype = C.c_int64
+    prod.lib.zxc_b200_plan_frame.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+    data = zc.silesia_shaped(1 << 20, seed=9)
+    rng = np.random.default_rng(5)
+    for bs, cks in ((4096, 0), (4096, 1), (65536, 1)):
+        fb = ref.compress(data, level=3, block_size=bs, checksum=cks, seekable=1).tobytes()
+        nb = (data.size + bs - 1) // bs
+        def plan(b):
+            jobs = (Job * nb)()
+            assert prod.lib.zxc_b200_plan_frame(b, len(b), jobs, nb, None) == nb
+            return [(j.src_off, j.dst_off, j.src_len, j.dst_cap) for j in jobs]
+        want = plan(fb)
+        ent0 = len(fb) - 12 - 4 * nb
+        assert fb[ent0 - 8] == 254  # the SEK block header
+        for kind in range(4):
+            b = bytearray(fb)
+            if kind == 0:
+                b[ent0:ent0 + 4 * nb] = bytes(4 * nb)
+            elif kind == 1:
+                b[ent0:ent0 + 4 * nb] = b"\xff" * (4 * nb)
+            elif kind == 2:
+                b[ent0:ent0 + 4 * nb] = rng.integers(0, 256, 4 * nb, dtype=np.uint8).tobytes()
+            else:
+                b[ent0:ent0 + 4 * nb] = np.full(nb, len(fb) // 2, dtype="<u4").tobytes()
+            assert plan(bytes(b)) == want
+
+
 def test_write_seek_table_matches_reference(prod, ref):
     sizes = np.array([22, 4000, 70000, 8, 123456], dtype="<u4")
     for lib in (prod.lib, ref.lib):

@@ -909,6 +909,9 @@ struct zxc_seekable_s {
     uint8_t dict_huf[ZXC_HUF_TABLE_SIZE];
     int has_dict_huf;
     zxg_ctx* gpu;
+    zxc_b200_job_t* jobs_buf; /* job and status tables of the last range call, kept: a million-block range would */
+    int32_t* st_buf;          /* otherwise fault in 28 MB of fresh pages on every call */
+    size_t tab_cap;
 };
 
 static int seekable_fetch(void* ctx, void* dst, size_t len, uint64_t off) {
@@ -950,6 +953,8 @@ void zxc_seekable_free(zxc_seekable* s) {
     if (!s) return;
     if (s->gpu) zxg_destroy(s->gpu);
     zxw_seek_free(&s->tab);
+    free(s->jobs_buf);
+    free(s->st_buf);
     free(s->dict);
     free(s->owned_reader_ctx);
     free(s);
@@ -1009,10 +1014,23 @@ static int64_t seekable_range(zxc_seekable* s, void* dst, size_t dst_capacity, u
     const uint64_t c_lo = s->tab.comp_offsets[b0], c_hi = s->tab.comp_offsets[b1 + 1];
     const uint64_t out_lo = (uint64_t)b0 * bs;
 
-    zxc_b200_job_t* jobs = (zxc_b200_job_t*)malloc((size_t)nb * sizeof *jobs);
-    int32_t* st = (int32_t*)malloc((size_t)nb * sizeof *st);
+    if (nb > s->tab_cap) {
+        free(s->jobs_buf);
+        free(s->st_buf);
+        s->jobs_buf = (zxc_b200_job_t*)malloc((size_t)nb * sizeof *s->jobs_buf);
+        s->st_buf = (int32_t*)malloc((size_t)nb * sizeof *s->st_buf);
+        s->tab_cap = (s->jobs_buf && s->st_buf) ? nb : 0;
+        if (!s->tab_cap) {
+            free(s->jobs_buf);
+            free(s->st_buf);
+            s->jobs_buf = NULL;
+            s->st_buf = NULL;
+            return ZXC_ERROR_MEMORY;
+        }
+    }
+    zxc_b200_job_t* jobs = s->jobs_buf;
+    int32_t* st = s->st_buf;
     int64_t ret;
-    if (!jobs || !st) { ret = ZXC_ERROR_MEMORY; goto out; }
     uint64_t out_bytes = 0;
     for (uint32_t i = 0; i < nb; i++) {
         jobs[i].src_off = s->tab.comp_offsets[b0 + i] - c_lo;
@@ -1076,8 +1094,6 @@ static int64_t seekable_range(zxc_seekable* s, void* dst, size_t dst_capacity, u
     rc = zxg_d2h(g, dst, d_out + (offset - out_lo), len);
     ret = rc != ZXC_OK ? rc : (int64_t)len;
 out:
-    free(jobs);
-    free(st);
     return ret;
 }
 

@@ -35,8 +35,34 @@ int zxw_walk(const uint8_t* src, size_t src_size, zxw_walk_t* w) {
     size_t ip = ZXC_FILE_HEADER_SIZE;
     uint32_t ghash = 0;
     w->end = ZXW_END_RAN_OFF;
+    /* The walk is a chain of dependent reads -- a header says where the next one is -- and the frame is cold in the
+     * caches: ~170 ns per block, 11 ms for the 65 536 blocks of a 4 GiB frame, all of it ahead of the first H2D copy.
+     * When the tail of the buffer looks like a seek table its entries predict where the headers are, so they are
+     * prefetched a few dozen blocks ahead.  Only a hint: every header is still read, CRC-checked and followed in
+     * order exactly as before, a wrong or forged table merely prefetches the wrong lines. */
+    const uint8_t* hint_ent = NULL;
+    uint64_t hint_n = 0, hint_idx = 0, hint_off = ZXC_FILE_HEADER_SIZE;
+    if (w->footer_size > 0 && fh.block_size > 0) {
+        const uint64_t nb = (w->footer_size + fh.block_size - 1) / fh.block_size;
+        const uint64_t sek_total = ZXF_BLOCK_HDR + nb * ZXF_SEEK_ENTRY;
+        if (nb <= 0xFFFFFFFFull && sek_total + ZXC_FILE_FOOTER_SIZE + ZXC_FILE_HEADER_SIZE <= src_size) {
+            const uint8_t* sek = src + (src_size - ZXC_FILE_FOOTER_SIZE - sek_total);
+            if (sek[0] == ZXF_BT_SEK && zxf_le32(sek + 3) == (uint32_t)(nb * ZXF_SEEK_ENTRY)) {
+                hint_ent = sek + ZXF_BLOCK_HDR;
+                hint_n = nb;
+            }
+        }
+    }
     while (ip < src_size) {
         const size_t rem = src_size - ip;
+        while (hint_idx < hint_n && hint_idx < n + 32) {
+            if (hint_off + ZXF_BLOCK_HDR <= src_size) {
+                __builtin_prefetch(src + hint_off - 4); /* the previous block's checksum trailer */
+                __builtin_prefetch(src + hint_off + ZXF_BLOCK_HDR - 1);
+            }
+            hint_off += zxf_le32(hint_ent + ZXF_SEEK_ENTRY * hint_idx);
+            hint_idx++;
+        }
         uint8_t type;
         uint32_t comp;
         if (zxf_read_block_header(src + ip, rem, &type, &comp) != ZXC_OK) {

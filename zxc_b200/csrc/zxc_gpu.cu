@@ -891,9 +891,9 @@ extern "C" int zxg_decode_pipelined(zxg_ctx* c, const uint8_t* h_src, uint64_t s
         }
         if (rc != ZXC_OK) return rc;
     }
-    if (cudaMemcpyAsync(d_jobs, h_jobs, (size_t)n_jobs * sizeof(zxc_b200_job_t), cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
-        return ZXC_B200_ERROR_CUDA;
-
+    /* the job table goes up chunk by chunk, just ahead of each launch: one copy of the whole table (24 MB for a million
+     * 4 KiB records, staged synchronously by the driver when the table is pageable) would sit in front of the first
+     * H2D of payload */
     const uint64_t chunk_target = (uint64_t)64 << 20; /* decoded bytes per pipeline stage */
     for (int i = 0; i < EV_RING; i++)
         if (!c->ev_ring[i] && cudaEventCreateWithFlags(&c->ev_ring[i], cudaEventDisableTiming) != cudaSuccess)
@@ -912,6 +912,9 @@ extern "C" int zxg_decode_pipelined(zxg_ctx* c, const uint8_t* h_src, uint64_t s
         if (cudaMemcpyAsync(d_in + (s0 - src_lo), h_src + s0, (size_t)(s1 - s0), cudaMemcpyHostToDevice, c->s_h2d) != cudaSuccess)
             rc = ZXC_B200_ERROR_CUDA;
         cudaEventRecord(ev_in, c->s_h2d);
+        if (cudaMemcpyAsync(d_jobs + j0, h_jobs + j0, (size_t)(j1 - j0) * sizeof(zxc_b200_job_t), cudaMemcpyHostToDevice,
+                            c->stream) != cudaSuccess)
+            rc = ZXC_B200_ERROR_CUDA;
         cudaStreamWaitEvent(c->stream, ev_in, 0);
         if (rc == ZXC_OK)
             rc = launch_decode(d_in - src_lo, d_out, d_jobs + j0, j1 - j0, d_status + j0, d_dict, dict_size, d_huf,
