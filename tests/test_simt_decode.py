@@ -1,0 +1,89 @@
+"""CPU tests of the decode kernels' SOURCE: zxc_b200/csrc/zxc_decode.cuh (and the headers it includes) compiled
+unchanged for the host on the fiber warp emulator of tests/simt/ -- one emulated warp per block runs decode_job()
+exactly as zxc_decode_kernel does, with the lanes resumed in a random order between warp-level primitives -- and
+compared with the unmodified reference (oracle/_ref) and the conformance vectors.  This is test infrastructure: it
+checks the kernels' logic where there is no GPU; the -m gpu tests check the compiled kernels through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+
+import zxc_corpus as zc
+import zxc_ctypes as z
+import zxc_simt as zs
+from test_oracle import CASES, G, GC_DICT, VALID, golden_dicts, make_case
+
+
+def _check(prod, frame, want, **kw):
+    st, out, oob, _ = zs.decode_frame(prod, frame, **kw)
+    assert oob == 0, "stores outside the destination"
+    assert all(s >= 0 for s in st), [z.ERR.get(s, s) for s in st if s < 0][:3]
+    assert np.array_equal(out, want)
+
+
+@pytest.mark.parametrize("kind,n", [(k, min(n, 1 << 20)) for k, n in CASES])
+@pytest.mark.parametrize("level", [1, 3, 5, 6, 7])
+def test_kernel_source_vs_reference(prod, ref, kind, n, level):
+    data = make_case(kind, n)
+    for bs, cks in ((4096, 1), (65536, 0), (2 << 20, 1)):
+        frame = ref.compress(data, level=level, block_size=bs, checksum=cks, seekable=1)
+        _check(prod, frame, data, verify=cks, seed=level * 131 + bs)
+
+
+@pytest.mark.parametrize("name", VALID)
+def test_kernel_source_conformance_vectors(prod, name):
+    frame = open(os.path.join(G, "valid", name + ".zxc"), "rb").read()
+    exp = np.frombuffer(open(os.path.join(G, "valid", name + ".expected"), "rb").read(), np.uint8)
+    did = int.from_bytes(frame[7:11], "little") if frame[6] & 0x40 else 0
+    d, h = golden_dicts().get(did, (None, None))
+    for units in (0, 1):  # sequence-centric body, then the output-centric one (small blocks / dictionaries use it)
+        _check(prod, frame, exp, dict=d, dict_huf=h, verify=1, units=units, seed=17 + units)
+
+
+def test_kernel_source_dictionary_records(prod, ref):
+    recs = zc.records(256 * 4096, record_size=4096, seed=7)
+    d = zc.train_dict_ref(ref, recs, record_size=4096, n_samples=128, cap=16384)
+    for level in (3, 5):
+        frame = ref.compress(recs, level=level, block_size=4096, checksum=0, seekable=1, dict=d)
+        for units in (0, 1):
+            _check(prod, frame, recs, dict=d, units=units, seed=5)
+
+
+def test_kernel_source_is_schedule_independent(prod, ref):
+    """same bytes whatever order the lanes run in between two warp primitives (seed 0 = lane order)"""
+    data = zc.silesia_shaped(1 << 19, seed=21)
+    frame = ref.compress(data, level=3, block_size=65536, checksum=0, seekable=1)
+    for seed in (0, 1, 2, 3, 99):
+        for units in (0, 1):
+            _check(prod, frame, data, units=units, seed=seed)
+
+
+def test_kernel_source_damaged_blocks_fail_like_the_reference(prod, ref):
+    """single-byte damage inside block payloads: a block the reference rejects is rejected with the same code by the
+    kernel source, a frame the reference still decodes gives the same bytes"""
+    data = zc.silesia_shaped(3 * 65536, seed=5)
+    rng = np.random.default_rng(11)
+    for level in (3, 6):
+        frame = ref.compress(data, level=level, block_size=65536, checksum=0, seekable=0)
+        fb = bytearray(frame.tobytes())
+        body_lo, body_hi = 16 + 8, len(fb) - 12 - 8
+        checked = 0
+        for _ in range(60):
+            pos = int(rng.integers(body_lo, body_hi))
+            b = bytearray(fb)
+            b[pos] ^= int(rng.integers(1, 256))
+            r_ref, out_ref = ref.decompress(bytes(b), data.size)
+            try:
+                st, out, oob, _ = zs.decode_frame(prod, bytes(b), seed=3)
+            except AssertionError:
+                continue  # the damage hit a block header: the host walk decides, not the kernel
+            assert oob == 0
+            if len(st) != 3:
+                continue
+            bad = [s for s, cap in zip(st, (65536, 65536, 65536)) if s < 0 or s != cap]
+            if r_ref == data.size:
+                assert not bad and np.array_equal(out, out_ref)
+            elif r_ref < 0 and bad and bad[0] < 0:
+                assert bad[0] == r_ref, (pos, z.ERR.get(bad[0], bad[0]), z.ERR.get(r_ref, r_ref))
+            checked += 1
+        assert checked >= 40
