@@ -41,7 +41,7 @@ def test_kernel_source_conformance_vectors(prod, name):
 
 
 def test_kernel_source_dictionary_records(prod, ref):
-    recs = zc.records(256 * 4096, record_size=4096, seed=7)
+    recs = zc.records(256, record_size=4096, seed=7)
     d = zc.train_dict_ref(ref, recs, record_size=4096, n_samples=128, cap=16384)
     for level in (3, 5):
         frame = ref.compress(recs, level=level, block_size=4096, checksum=0, seekable=1, dict=d)
@@ -83,7 +83,12 @@ def test_kernel_source_damaged_blocks_fail_like_the_reference(prod, ref):
             bad = [s for s, cap in zip(st, (65536, 65536, 65536)) if s < 0 or s != cap]
             if r_ref == data.size:
                 assert not bad and np.array_equal(out, out_ref)
-            elif r_ref < 0 and bad and bad[0] < 0:
-                assert bad[0] == r_ref, (pos, z.ERR.get(bad[0], bad[0]), z.ERR.get(r_ref, r_ref))
+            else:
+                assert bad, (pos, "the reference rejects, the kernel source accepts")
+                if bad[0] < 0:
+                    # a block that outgrows its room is OVERFLOW for the kernel; the host turns it into the reference's
+                    # DST_TOO_SMALL where the frame driver would have (zxc_api.c), so the two count as one here
+                    room = {-2: -10}
+                    assert room.get(bad[0], bad[0]) == room.get(r_ref, r_ref), (pos, z.ERR.get(bad[0], bad[0]), z.ERR.get(r_ref, r_ref))
             checked += 1
         assert checked >= 40
