@@ -11,7 +11,7 @@ import zxc_ctypes as z
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SIMT_DIR = os.path.join(HERE, "simt")
-SIMT_SO = os.path.join(SIMT_DIR, "libzxc_simt_decode.so")
+SIMT_SO = os.environ.get("ZXC_SIMT_SO") or os.path.join(SIMT_DIR, "libzxc_simt_decode.so")  # variant builds: make SO=... EXTRA=-D...
 
 
 class Job(C.Structure):
@@ -24,6 +24,8 @@ class Info(C.Structure):
 
 
 def build():
+    if os.environ.get("ZXC_SIMT_SO"):
+        return
     r = subprocess.run(["make", "-s"], cwd=SIMT_DIR, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout
 

@@ -92,6 +92,33 @@ __device__ __forceinline__ u32 warp_incl_scan(u32 v, u32 lane) {
     return v;
 }
 
+/* Explicit shared-memory stores.  With the ring as an ordinary pointer ptxas re-derives the CTA's shared window base
+ * (S2R SR_CgaCtaId, MOV, LEA, IADD) in front of every predicated STS of the copy helpers instead of holding it in a
+ * register -- four extra instructions per store.  A 32-bit shared address made opaque once per block cannot be
+ * re-derived, so it stays in a register (or one LDL away).  The host versions serve the CPU emulator (tests/simt). */
+#ifdef __CUDACC__
+__device__ __forceinline__ u32 smem_addr(const void* p) {
+    u32 a = (u32)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a));
+    return a;
+}
+template <int OFF> __device__ __forceinline__ void sts32(u32 a, u32 v) {
+    asm volatile("st.shared.u32 [%0+%2], %1;" ::"r"(a), "r"(v), "n"(OFF) : "memory");
+}
+template <int OFF> __device__ __forceinline__ void sts16(u32 a, u32 v) {
+    asm volatile("st.shared.u16 [%0+%2], %1;" ::"r"(a), "h"((unsigned short)v), "n"(OFF) : "memory");
+}
+template <int OFF> __device__ __forceinline__ void sts8(u32 a, u32 v) {
+    asm volatile("st.shared.u8 [%0+%2], %1;" ::"r"(a), "r"(v), "n"(OFF) : "memory");
+}
+#else
+extern u8 smem[];
+static inline u32 smem_addr(const void* p) { return (u32)(reinterpret_cast<const u8*>(p) - smem); }
+template <int OFF> static inline void sts32(u32 a, u32 v) { memcpy(smem + a + OFF, &v, 4); }
+template <int OFF> static inline void sts16(u32 a, u32 v) { const unsigned short h = (unsigned short)v; memcpy(smem + a + OFF, &h, 2); }
+template <int OFF> static inline void sts8(u32 a, u32 v) { smem[a + OFF] = (u8)v; }
+#endif
+
 #include "zxc_huffman.cuh"
 
 /* per-warp scratch layout (bytes), a function of the launch's block_cap */
@@ -447,9 +474,17 @@ __device__ __forceinline__ void warp_match_to_ring(const Window& w, u32 d, u32 o
             __syncwarp();
         }
     } else {
-        /* period-`off` replication of the complete window [d-off, d) */
-        for (u32 k = lane; k < n; k += 32)
-            w.ring[(d + k) & mask] = window_byte(w, (i32)d - (i32)off + (i32)(k % off));
+        /* period-`off` replication of the complete window [d-off, d): lane r holds window byte r, byte k of the match
+         * is window byte k mod off -- fetched by shuffle, the residue stepped by 32 mod off (no division per byte) */
+        const u32 mine = lane < off ? (u32)window_byte(w, (i32)d - (i32)off + (i32)lane) : 0u;
+        const u32 step = 32u % off;
+        u32 r = lane % off;
+        for (u32 c = 0; c < n; c += 32) {
+            const u32 b = __shfl_sync(FULL, mine, r);
+            if (c + lane < n) w.ring[(d + c + lane) & mask] = (u8)b;
+            r += step;
+            if (r >= off) r -= off;
+        }
     }
 }
 
@@ -514,6 +549,67 @@ __device__ __forceinline__ void lane_copy_words(u8* ring, u32 dpos, const u8* sp
 }
 
 /* ------------------------------------------------------------------------- */
+/* the same copy without byte loads and without branches (ZXC_LANECOPY2): the   */
+/* NWORDS + 1 aligned source words that cover the item are loaded once, shifted  */
+/* onto the destination grid in registers, and the partial words at either end   */
+/* leave as byte / halfword stores of those registers (a neighbouring lane owns  */
+/* the other bytes of such a word, so no read-modify-write).  Same contract as    */
+/* lane_copy_words; reads up to 3 bytes before sp and 7 past sp + n.              */
+/* ------------------------------------------------------------------------- */
+template <int NWORDS>
+__device__ __forceinline__ void lane_copy_words2(u32 ring_s, u32 dpos, const u8* sp, u32 n, bool on) {
+    if (on) {
+        const u32 da = dpos & 3u;
+        const u32 e = da + n;              /* end of the item, in bytes from the start of destination word 0 */
+        const u32 kt = e >> 2;             /* words below kt are whole (word 0 only if da == 0) ... */
+        const u32 tb = e & 3u;             /* ... word kt holds the last tb bytes */
+        const u8* bp = sp - da;
+        const u32 m = (u32)(reinterpret_cast<uintptr_t>(bp)) & 3u;
+        const u32* wp = reinterpret_cast<const u32*>(bp - m);
+        const u32 sh = m * 8u;
+        const u32 nsrc = kt + (tb ? 1u : 0u) + (m ? 1u : 0u);
+        u32 W[NWORDS + 1];
+#pragma unroll
+        for (int k = 0; k <= NWORDS; k++) W[k] = (u32)k < nsrc ? wp[k] : 0u;
+        u32 D[NWORDS];
+#pragma unroll
+        for (int k = 0; k < NWORDS; k++) D[k] = __funnelshift_r(W[k], W[k + 1], sh);
+        const u32 d0 = ring_s + (dpos & (RING_BYTES - 1)) - da; /* destination word 0 */
+        /* whole words */
+        if (da == 0 && kt > 0) sts32<0>(d0, D[0]);
+        if (1 < kt) sts32<4>(d0, D[1]);
+        if (NWORDS > 2 && 2 < kt) sts32<8>(d0, D[NWORDS > 2 ? 2 : 0]);
+        if (NWORDS > 3 && 3 < kt) sts32<12>(d0, D[NWORDS > 3 ? 3 : 0]);
+        if (NWORDS > 4 && 4 < kt) sts32<16>(d0, D[NWORDS > 4 ? 4 : 0]);
+        if (NWORDS > 5 && 5 < kt) sts32<20>(d0, D[NWORDS > 5 ? 5 : 0]);
+        if (NWORDS > 6 && 6 < kt) sts32<24>(d0, D[NWORDS > 6 ? 6 : 0]);
+        if (NWORDS > 7 && 7 < kt) sts32<28>(d0, D[NWORDS > 7 ? 7 : 0]);
+        static_assert(NWORDS >= 2 && NWORDS <= 8, "the store ladder above is written out for two to eight words");
+        /* head of word 0: bytes [da, min(4, e)) when da != 0, as a byte mask */
+        {
+            const u32 e0 = e < 4u ? e : 4u;
+            const u32 bm = da ? ((0xFu << da) & (0xFu >> (4u - e0))) : 0u;
+            if (bm & 2u) sts8<1>(d0, D[0] >> 8);
+            if ((bm & 0xCu) == 0xCu) sts16<2>(d0, D[0] >> 16);
+            if ((bm & 0xCu) == 0x4u) sts8<2>(d0, D[0] >> 16);
+            if ((bm & 0xCu) == 0x8u) sts8<3>(d0, D[0] >> 24);
+        }
+        /* tail: the first tb bytes of word kt (word 0 with da != 0 was the head's business) */
+        {
+            u32 tv = D[0];
+#pragma unroll
+            for (int k = 1; k < NWORDS; k++)
+                if (kt == (u32)k) tv = D[k];
+            const u32 tm = (kt > 0u || da == 0u) ? tb : 0u;
+            const u32 dt = d0 + 4u * kt;
+            if (tm == 1u) sts8<0>(dt, tv);
+            if (tm >= 2u) sts16<0>(dt, tv);
+            if (tm == 3u) sts8<2>(dt, tv >> 16);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------- */
 /* long items, four at a time: each 8-lane group copies one item into the ring,  */
 /* 32 bytes per step (lane = destination word).  Items of one call are mutually  */
 /* independent; an item may overlap itself only at distance >= 36.  Owners hold   */
@@ -566,8 +662,102 @@ __device__ __forceinline__ void group4_copy_words(u8* ring, u32 m_items, u32 my_
     }
 }
 
-#define LIT_SHORT 20u
-#define MATCH_SHORT 20u
+/* ------------------------------------------------------------------------- */
+/* long items of one pass, all at once (ZXC_BALANCED): every aligned run of four  */
+/* whole destination words of every item is one lane's work, so a pass moves up   */
+/* to 512 bytes per step and -- what matters -- pays ONE memory round trip per    */
+/* step: group4_copy_words above moves 32 bytes of an item per round trip (its    */
+/* loop must order each step's loads behind the previous step's stores), and two  */
+/* thirds of the corpus' bytes sit in items longer than 64 bytes that come from   */
+/* global memory.  Items of one call are mutually independent and do not overlap  */
+/* themselves (distance >= length), so no chunk reads what another one writes;    */
+/* the aligned words a chunk loads may reach 3 bytes into a neighbour's           */
+/* destination, those bytes are shifted out.  Owners hold (dpos, source, n).      */
+/* ------------------------------------------------------------------------- */
+__device__ __forceinline__ void balanced_copy_words(u32 ring_s, u32 m_items, u32 my_d, const u8* my_sp, u32 my_n,
+                                                    u32 lane) {
+    const bool own = (m_items >> lane) & 1u;
+    const u32 o_da = my_d & 3u;
+    const u32 o_ff = o_da ? 1u : 0u;
+    const u32 o_lfe = (o_da + my_n) >> 2;
+    const u32 o_tb = (o_da + my_n) & 3u;
+    const u32 o_dbyte = ring_s + (my_d & (RING_BYTES - 1));
+    /* edge bytes by the owner: the head of destination word 0, the tail of word lfe (items here are > 20 bytes) */
+    if (own && o_da) {
+        sts8<0>(o_dbyte, my_sp[0]);
+        if (o_da < 3) sts8<1>(o_dbyte, my_sp[1]);
+        if (o_da < 2) sts8<2>(o_dbyte, my_sp[2]);
+    }
+    if (own && o_tb) {
+        const u32 t0 = my_n - o_tb;
+        sts8<0>(o_dbyte + t0, my_sp[t0]);
+        if (o_tb > 1) sts8<1>(o_dbyte + t0, my_sp[t0 + 1]);
+        if (o_tb > 2) sts8<2>(o_dbyte + t0, my_sp[t0 + 2]);
+    }
+    const u32 c = own ? (o_lfe - o_ff + 3u) >> 2 : 0u; /* chunks of four whole words */
+    const u32 incl = warp_incl_scan(c, lane);
+    const u32 total = __shfl_sync(FULL, incl, 31);
+    const u32 excl = incl - c;
+    const u32 pk = (my_d & (RING_BYTES - 1)) | (my_n << 16); /* ring offset < 64 Ki, n <= RING_LIMIT */
+    const unsigned long long my_sp64 = reinterpret_cast<unsigned long long>(my_sp);
+    for (u32 base = 0; base < total; base += 32) {
+        const u32 q = base + lane;
+        const bool act = q < total;
+        u32 lo = 0, hi = 31; /* owner = first lane whose inclusive count exceeds q */
+#pragma unroll
+        for (int it = 0; it < 5; it++) {
+            const u32 mid = (lo + hi) >> 1;
+            const u32 v = __shfl_sync(FULL, incl, mid);
+            if (v > q) hi = mid;
+            else lo = mid + 1;
+        }
+        const u32 j = lo & 31u;
+        const u32 k = q - __shfl_sync(FULL, excl, j);
+        const u32 pj = __shfl_sync(FULL, pk, j);
+        const u8* sp = reinterpret_cast<const u8*>(__shfl_sync(FULL, my_sp64, j));
+        if (act) {
+            const u32 da = pj & 3u;
+            const u32 n = pj >> 16;
+            const u32 lfe = (da + n) >> 2;
+            const u32 w0 = (da ? 1u : 0u) + 4u * k;
+            const u8* bp = sp - da;
+            const u32 m = (u32)(reinterpret_cast<uintptr_t>(bp)) & 3u;
+            const u32* wp = reinterpret_cast<const u32*>(bp - m) + w0;
+            const u32 dw = ring_s + (pj & 0xFFFFu) - da + 4u * w0;
+            const u32 sh = m * 8u;
+            const u32 left = lfe - w0;            /* whole words from w0 on, >= 1 */
+            const u32 nsrc = left + (m ? 1u : 0u);
+            u32 W[5];
+#pragma unroll
+            for (int i = 0; i < 5; i++) W[i] = (u32)i < nsrc ? wp[i] : 0u;
+            sts32<0>(dw, __funnelshift_r(W[0], W[1], sh));
+            if (1 < left) sts32<4>(dw, __funnelshift_r(W[1], W[2], sh));
+            if (2 < left) sts32<8>(dw, __funnelshift_r(W[2], W[3], sh));
+            if (3 < left) sts32<12>(dw, __funnelshift_r(W[3], W[4], sh));
+        }
+    }
+}
+
+#ifndef ZXC_BALANCED
+#define ZXC_BALANCED 1
+#endif
+#ifndef ZXC_LANECOPY2
+#define ZXC_LANECOPY2 1
+#endif
+#ifndef ZXC_OPAQUE_LANE
+#define ZXC_OPAQUE_LANE 0
+#endif
+#ifndef ZXC_MERGE_PASS0
+#define ZXC_MERGE_PASS0 0
+#endif
+#ifndef ZXC_TOKPF
+#define ZXC_TOKPF 0
+#endif
+#ifndef ZXC_NW
+#define ZXC_NW 6 /* destination words a per-lane copy may touch: items up to 4 * ZXC_NW - 4 bytes are "short" */
+#endif
+#define LIT_SHORT (4u * ZXC_NW - 4u)
+#define MATCH_SHORT (4u * ZXC_NW - 4u)
 
 /* ------------------------------------------------------------------------- */
 /* GLO / GHI block body.  Returns decoded bytes or a negative zxc_error_t.    */
@@ -613,6 +803,8 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
     w.dict = dict;
     w.dict_size = dict_size;
     w.near_lo = 0;
+    const u32 ring_s = smem_addr(ring);
+    (void)ring_s;
     u32 O = 0, L = 0, F = 0, epos = 0, ring_lo = 0;
 
     /* Escape values for the whole block up front (segment-map scan over the extras section, zxc_decode2_core.h):
@@ -643,11 +835,36 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
     }
 
     u32 base = 0;
+#if ZXC_TOKPF
+    u32 nx_a = 0, nx_b = 0, nx_base = 0xFFFFFFFFu;
+#endif
     while (base < n_seq) {
         /* ---- unpack tokens and offsets ---- */
         const u32 i = base + lane;
         const bool valid = i < n_seq;
         u32 ll = 0, ml = 0, off = 1;
+#if ZXC_TOKPF
+        u32 a = nx_a, b = nx_b;
+        if (nx_base != base && valid) { /* the previous batch stopped short of 32 sequences: its look-ahead is off */
+            b = 0;
+            if (!ghi) {
+                a = tok[i];
+                b = enc_off ? (u32)offs[i] : ld16(offs + 2 * (size_t)i);
+            } else {
+                a = ld32(tok + 4 * (size_t)i);
+            }
+        }
+        nx_base = base + 32; /* look ahead: the next batch's tokens and offsets travel while this batch copies */
+        if (i + 32 < n_seq) {
+            if (!ghi) {
+                nx_a = tok[i + 32];
+                nx_b = enc_off ? (u32)offs[i + 32] : ld16(offs + 2 * (size_t)(i + 32));
+            } else {
+                nx_a = ld32(tok + 4 * (size_t)(i + 32));
+            }
+        }
+        if (valid) {
+#else
         if (valid) {
             u32 a, b = 0;
             if (!ghi) {
@@ -656,6 +873,7 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
             } else {
                 a = ld32(tok + 4 * (size_t)i);
             }
+#endif
             if (!ghi) {
                 ll = a >> 4;
                 ml = a & 15;
@@ -758,7 +976,11 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
                                (near ? (si >= 8 && si + ml + 8 <= RING_BYTES)
                                      : (src_lo >= 8 && src_lo + (i32)ml + 4 <= w.near_lo));
         const bool m_lane_ok = m_word_ok && ml <= MATCH_SHORT && off >= ml;
+#if ZXC_BALANCED
+        const bool m_grp_ok = m_word_ok && !m_lane_ok && off >= ml; /* chunks of one item run side by side */
+#else
         const bool m_grp_ok = m_word_ok && !m_lane_ok && off >= 36;
+#endif
         const u8* m_sp = near ? ring + si : out + src_lo;
         const bool l_word_ok = (out_start & mask) + ll + 4 <= RING_BYTES;
 
@@ -791,13 +1013,17 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
             bool ready, lok, gok;
             u32 it_d, it_n;
             const u8* it_sp;
+            bool m0 = false; /* pass 0, lane without literals: its match goes now if the source lies before this batch */
             if (lit_pass) {
-                ready = act && ll > 0;
-                it_d = out_start;
-                it_n = ll;
-                it_sp = lit + lit_start;
-                lok = l_word_ok && ll <= LIT_SHORT;
-                gok = l_word_ok && ll > LIT_SHORT;
+#if ZXC_MERGE_PASS0
+                m0 = act && ll == 0 && src_end <= (i32)O;
+#endif
+                ready = (act && ll > 0) || m0;
+                it_d = m0 ? mdst : out_start;
+                it_n = m0 ? ml : ll;
+                it_sp = m0 ? m_sp : lit + lit_start;
+                lok = m0 ? m_lane_ok : (l_word_ok && ll <= LIT_SHORT);
+                gok = m0 ? m_grp_ok : (l_word_ok && ll > LIT_SHORT);
             } else {
                 ready = ((pending >> lane) & 1u) && (pending & depmask) == 0;
                 it_d = mdst;
@@ -806,24 +1032,38 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
                 lok = m_lane_ok;
                 gok = m_grp_ok;
             }
-            lane_copy_words<6>(ring, it_d, it_sp, it_n, ready && lok);
+#if ZXC_LANECOPY2
+            lane_copy_words2<ZXC_NW>(ring_s, it_d, it_sp, it_n, ready && lok);
+#else
+            lane_copy_words<ZXC_NW>(ring, it_d, it_sp, it_n, ready && lok);
+#endif
             const u32 m_grp = __ballot_sync(FULL, ready && gok);
+#if ZXC_BALANCED
+            if (m_grp) balanced_copy_words(ring_s, m_grp, it_d, it_sp, it_n, lane);
+#else
             if (m_grp) group4_copy_words(ring, m_grp, it_d, it_sp, it_n, lane);
+#endif
             u32 m_slow = __ballot_sync(FULL, ready && !lok && !gok);
             while (m_slow) { /* ring wrap, close overlap, dictionary, straddling sources: byte paths */
                 const int j = __ffs(m_slow) - 1;
                 m_slow &= m_slow - 1;
                 const u32 d = __shfl_sync(FULL, it_d, j), n = __shfl_sync(FULL, it_n, j);
-                const u32 aux = __shfl_sync(FULL, lit_pass ? lit_start : off, j);
-                if (lit_pass) {
-                    for (u32 k = lane; k < n; k += 32) ring[(d + k) & mask] = lit[aux + k];
+                const bool as_lit = lit_pass && !m0;
+                const u32 aux = __shfl_sync(FULL, (as_lit ? lit_start : off) | (as_lit ? 0x80000000u : 0u), j);
+                if (aux >> 31) {
+                    for (u32 k = lane; k < n; k += 32) ring[(d + k) & mask] = lit[(aux & 0x7FFFFFFFu) + k];
                 } else {
                     warp_match_to_ring(w, d, aux, n, lane);
                 }
             }
             __syncwarp();
+#if ZXC_MERGE_PASS0
+            pending &= ~__ballot_sync(FULL, lit_pass ? m0 : ready);
+            lit_pass = false;
+#else
             if (lit_pass) lit_pass = false;
             else pending &= ~__ballot_sync(FULL, ready);
+#endif
             if (!pending) break;
         }
 
@@ -889,7 +1129,11 @@ __device__ int decode_job(const DecodeParams& P, const zxc_b200_job_t& job, u8* 
 template <bool UNITS, bool DEFERRED>
 __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) zxc_decode_kernel(const DecodeParams P) {
     extern __shared__ __align__(16) u8 smem[];
-    const u32 lane = threadIdx.x & 31;
+    u32 lane_id = threadIdx.x & 31;
+#if ZXC_OPAQUE_LANE && defined(__CUDACC__)
+    asm volatile("" : "+r"(lane_id)); /* keep the lane number in a register: ptxas otherwise re-reads SR_TID.X at its uses */
+#endif
+    const u32 lane = lane_id;
     const u32 wic = threadIdx.x >> 5;
     const u32 gwarp = blockIdx.x * WARPS_PER_CTA + wic;
     u8* scratch = P.scratch + (size_t)gwarp * P.scratch_stride + 256; /* lead-in: word loads may start below */
