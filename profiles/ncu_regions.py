@@ -4,13 +4,16 @@ import csv, sys, subprocess, collections
 rep = sys.argv[1]
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
-REG = [(1, 160, "helpers ld16/ld32/scan/varint"), (161, 217, "checksum"), (218, 241, "rle"), (242, 357, "parse_sections"),
-       (358, 378, "window_byte"), (379, 405, "ring_flush"), (406, 438, "warp_copy_words (unused)"), (439, 468, "slow match paths"),
-       (469, 515, "lane_copy_words"), (516, 568, "group4_copy_words"), (569, 645, "block prologue/extras prepass"),
-       (646, 668, "unpack tok/off"), (669, 691, "escapes"), (692, 703, "scans"), (704, 731, "giant"), (732, 746, "validation"),
-       (747, 764, "classify"), (765, 786, "depmask"), (787, 808, "pass loop head"), (809, 809, "call lane_copy"),
-       (810, 811, "grp ballot/call"), (812, 824, "slow dispatch"), (825, 829, "pass loop tail"), (830, 849, "advance/flush call"),
-       (850, 858, "trailing literals"), (859, 888, "decode_job"), (889, 943, "kernel loop"), (944, 2000, "other")]
+import re, os
+SRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "zxc_b200", "csrc", "zxc_decode.cuh")
+marks = []  # (line, name): function definitions and the "---- section ----" comments of decode_lz_block
+for i, line in enumerate(open(SRC), 1):
+    m = re.match(r"(?:template <[^>]*>\s*)?(?:__device__|__global__|static inline)[^(]*?(\w+)\(", line)
+    if m and not line.startswith(" "): marks.append((i, m.group(1)))
+    m = re.match(r"\s+/\* ---- (.*?)(?: ----|:|\(|$)", line)
+    if m: marks.append((i, "· " + m.group(1).strip()[:40]))
+marks.sort()
+REG = [(1, marks[0][0] - 1, "preamble")] + [(a, (marks[k + 1][0] - 1) if k + 1 < len(marks) else 10 ** 6, n) for k, (a, n) in enumerate(marks)]
 cur_file = None
 agg = collections.Counter(); st = collections.Counter(); other = collections.Counter(); ost = collections.Counter()
 hdr = None
@@ -29,6 +32,7 @@ for x in rows:
         other[k] += n; ost[k] += w
 tot = sum(agg.values()) + sum(other.values()); tots = (sum(st.values()) + sum(ost.values())) or 1
 print("total inst", tot)
+seen = set()
 for lo, hi, name in REG:
-    if agg[name]: print(f"{100*agg[name]/tot:5.1f}% inst {100*st[name]/tots:5.1f}% stall | {name} (L{lo}-{hi})")
+    if agg[name] and name not in seen: print(f"{100*agg[name]/tot:5.1f}% inst {100*st[name]/tots:5.1f}% stall | {name} (L{lo}-)"); seen.add(name)
 for k, n in other.most_common(10): print(f"{100*n/tot:5.1f}% inst {100*ost[k]/tots:5.1f}% stall | file {k}")

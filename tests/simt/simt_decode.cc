@@ -11,6 +11,9 @@
 
 #include <vector>
 
+extern "C" { uint64_t simt_stat[32]; }
+#define ZXC_STAT(i, v) do { const uint64_t zv_ = (uint64_t)(v); if (simt::g_warp->current == 0) simt_stat[i] += zv_; } while (0)
+
 #include "zxc_decode.cuh"
 
 alignas(16) u8 smem[WARPS_PER_CTA * RING_BYTES];

@@ -31,6 +31,9 @@ typedef uint64_t u64;
 typedef int32_t i32;
 
 #define FULL 0xFFFFFFFFu
+#ifndef ZXC_STAT
+#define ZXC_STAT(i, v) /* tests/simt counts events here (lane 0 only); nothing in the product build */
+#endif
 #ifndef WARPS_PER_CTA
 #define WARPS_PER_CTA 4
 #endif
@@ -556,6 +559,15 @@ __device__ __forceinline__ void lane_copy_words(u8* ring, u32 dpos, const u8* sp
 /* the other bytes of such a word, so no read-modify-write).  Same contract as    */
 /* lane_copy_words; reads up to 3 bytes before sp and 7 past sp + n.              */
 /* ------------------------------------------------------------------------- */
+/* whole words K .. N-1 of a per-lane copy: word k is stored when k < kt (constant offsets, unrolled at compile time) */
+template <int K, int N>
+__device__ __forceinline__ void store_ladder(u32 d0, const u32* D, u32 kt) {
+    if constexpr (K < N) {
+        if ((u32)K < kt) sts32<4 * K>(d0, D[K]);
+        store_ladder<K + 1, N>(d0, D, kt);
+    }
+}
+
 template <int NWORDS>
 __device__ __forceinline__ void lane_copy_words2(u32 ring_s, u32 dpos, const u8* sp, u32 n, bool on) {
     if (on) {
@@ -577,14 +589,7 @@ __device__ __forceinline__ void lane_copy_words2(u32 ring_s, u32 dpos, const u8*
         const u32 d0 = ring_s + (dpos & (RING_BYTES - 1)) - da; /* destination word 0 */
         /* whole words */
         if (da == 0 && kt > 0) sts32<0>(d0, D[0]);
-        if (1 < kt) sts32<4>(d0, D[1]);
-        if (NWORDS > 2 && 2 < kt) sts32<8>(d0, D[NWORDS > 2 ? 2 : 0]);
-        if (NWORDS > 3 && 3 < kt) sts32<12>(d0, D[NWORDS > 3 ? 3 : 0]);
-        if (NWORDS > 4 && 4 < kt) sts32<16>(d0, D[NWORDS > 4 ? 4 : 0]);
-        if (NWORDS > 5 && 5 < kt) sts32<20>(d0, D[NWORDS > 5 ? 5 : 0]);
-        if (NWORDS > 6 && 6 < kt) sts32<24>(d0, D[NWORDS > 6 ? 6 : 0]);
-        if (NWORDS > 7 && 7 < kt) sts32<28>(d0, D[NWORDS > 7 ? 7 : 0]);
-        static_assert(NWORDS >= 2 && NWORDS <= 8, "the store ladder above is written out for two to eight words");
+        store_ladder<1, NWORDS>(d0, D, kt);
         /* head of word 0: bytes [da, min(4, e)) when da != 0, as a byte mask */
         {
             const u32 e0 = e < 4u ? e : 4u;
@@ -701,6 +706,7 @@ __device__ __forceinline__ void balanced_copy_words(u32 ring_s, u32 m_items, u32
     const u32 pk = (my_d & (RING_BYTES - 1)) | (my_n << 16); /* ring offset < 64 Ki, n <= RING_LIMIT */
     const unsigned long long my_sp64 = reinterpret_cast<unsigned long long>(my_sp);
     for (u32 base = 0; base < total; base += 32) {
+        ZXC_STAT(8, 1); /* balanced steps */
         const u32 q = base + lane;
         const bool act = q < total;
         u32 lo = 0, hi = 31; /* owner = first lane whose inclusive count exceeds q */
@@ -747,14 +753,43 @@ __device__ __forceinline__ void balanced_copy_words(u32 ring_s, u32 m_items, u32
 #ifndef ZXC_OPAQUE_LANE
 #define ZXC_OPAQUE_LANE 0
 #endif
-#ifndef ZXC_MERGE_PASS0
-#define ZXC_MERGE_PASS0 0
+#ifndef ZXC_PF_STREAM
+#define ZXC_PF_STREAM 0
 #endif
-#ifndef ZXC_TOKPF
-#define ZXC_TOKPF 0
+#ifndef ZXC_PF_FAR
+#define ZXC_PF_FAR 0
+#endif
+#if defined(__CUDACC__)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#else
+static inline void prefetch_l2(const void*) {}
+static inline void prefetch_l1(const void*) {}
+#endif
+#ifndef ZXC_COLD_CALLS
+#define ZXC_COLD_CALLS 0
+#endif
+#if ZXC_COLD_CALLS
+/* the byte paths of the pass loop as one out-of-line call: they serve a few items per block, and inlined they sit in
+ * the middle of the loop the instruction cache has to hold */
+__device__ __noinline__ void slow_item(u8* ring, u8* out, const u8* dict, u32 dict_size, i32 near_lo, const u8* lit,
+                                       u32 d, u32 n, u32 aux, u32 lane) {
+    if (lit) {
+#pragma unroll 1
+        for (u32 k = lane; k < n; k += 32) ring[(d + k) & (RING_BYTES - 1)] = lit[aux + k];
+    } else {
+        Window w;
+        w.ring = ring;
+        w.out = out;
+        w.dict = dict;
+        w.dict_size = dict_size;
+        w.near_lo = near_lo;
+        warp_match_to_ring(w, d, aux, n, lane);
+    }
+}
 #endif
 #ifndef ZXC_NW
-#define ZXC_NW 6 /* destination words a per-lane copy may touch: items up to 4 * ZXC_NW - 4 bytes are "short" */
+#define ZXC_NW 8 /* destination words a per-lane copy may touch: items up to 4 * ZXC_NW - 4 bytes are "short" (6: -3.6 %, 10: +0.1 %) */
 #endif
 #define LIT_SHORT (4u * ZXC_NW - 4u)
 #define MATCH_SHORT (4u * ZXC_NW - 4u)
@@ -775,11 +810,8 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
     const u8* ext = S.ext;
     const u32 ext_end = S.ext_end, n_lit_avail = S.n_lit_avail, n_seq = S.n_seq, enc_off = S.enc_off;
 
-    /* Output-centric body (zxc_decode_units.cuh) where it measured faster than the sequence-centric one below:
-     * dictionary decodes of small blocks (BASELINE configs[3]: 298 vs 152 GB/s on 4 KiB records) -- dictionary
-     * sources are plain 16-byte gathers there, byte paths here.  At 64 KiB blocks without a dictionary it is the
-     * slower one (156 vs 307 GB/s), see DESIGN.md.  The launch picks the kernel instance (launch_decode);
-     * ZXC_B200_UNITS=1 / 0 forces it on / off. */
+    /* Output-centric body (zxc_decode_units.cuh): only in the <UNITS = true> instance, which the launch picks on request
+     * (ZXC_B200_UNITS=1); the sequence-centric body below is the faster one on every workload measured. */
     (void)P_flags;
     if (UNITS && cap <= 65536u) { /* its tables go where the scratch is idle */
         u8* tok_buf = scratch + scr_lit_cap(scratch_cap);
@@ -835,36 +867,11 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
     }
 
     u32 base = 0;
-#if ZXC_TOKPF
-    u32 nx_a = 0, nx_b = 0, nx_base = 0xFFFFFFFFu;
-#endif
     while (base < n_seq) {
         /* ---- unpack tokens and offsets ---- */
         const u32 i = base + lane;
         const bool valid = i < n_seq;
         u32 ll = 0, ml = 0, off = 1;
-#if ZXC_TOKPF
-        u32 a = nx_a, b = nx_b;
-        if (nx_base != base && valid) { /* the previous batch stopped short of 32 sequences: its look-ahead is off */
-            b = 0;
-            if (!ghi) {
-                a = tok[i];
-                b = enc_off ? (u32)offs[i] : ld16(offs + 2 * (size_t)i);
-            } else {
-                a = ld32(tok + 4 * (size_t)i);
-            }
-        }
-        nx_base = base + 32; /* look ahead: the next batch's tokens and offsets travel while this batch copies */
-        if (i + 32 < n_seq) {
-            if (!ghi) {
-                nx_a = tok[i + 32];
-                nx_b = enc_off ? (u32)offs[i + 32] : ld16(offs + 2 * (size_t)(i + 32));
-            } else {
-                nx_a = ld32(tok + 4 * (size_t)(i + 32));
-            }
-        }
-        if (valid) {
-#else
         if (valid) {
             u32 a, b = 0;
             if (!ghi) {
@@ -873,7 +880,6 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
             } else {
                 a = ld32(tok + 4 * (size_t)i);
             }
-#endif
             if (!ghi) {
                 ll = a >> 4;
                 ml = a & 15;
@@ -957,6 +963,15 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
             return __shfl_sync(FULL, code, __ffs(m_err) - 1);
         }
         const u32 T = __shfl_sync(FULL, s_tot, m - 1), TL = __shfl_sync(FULL, s_ll, m - 1);
+#if ZXC_PF_STREAM
+        /* the three input streams advance linearly: ask for the sectors the next batches will read while this one copies */
+        if (lane < 4) {
+            const u8* p = lane == 0 ? tok + (size_t)(ghi ? 4u : 1u) * (base + ZXC_PF_STREAM * 32u)
+                        : lane == 1 ? (offs ? offs + (size_t)(enc_off ? 1u : 2u) * (base + ZXC_PF_STREAM * 32u) : tok)
+                                    : lit + L + TL + 128u * (lane - 2u) + 64u * ZXC_PF_STREAM;
+            prefetch_l2(p);
+        }
+#endif
         {
             const i32 a = (i32)(O + T) - (i32)RING_BYTES + 32;
             w.near_lo = a > (i32)ring_lo ? a : (i32)ring_lo;
@@ -972,16 +987,22 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
          * ring (no wrap) or entirely flushed to global memory */
         const bool near = src_lo >= w.near_lo;
         const u32 si = (u32)src_lo & mask;
+        /* a source that lies inside the dictionary, 8 bytes clear of either end (the aligned word loads reach that far),
+         * is a global source like any other */
+        const bool in_dict = src_lo + (i32)ml + 8 <= 0 && (i32)dict_size + src_lo >= 8;
         const bool m_word_ok = ((mdst & mask) + ml + 4 <= RING_BYTES) &&
                                (near ? (si >= 8 && si + ml + 8 <= RING_BYTES)
-                                     : (src_lo >= 8 && src_lo + (i32)ml + 4 <= w.near_lo));
+                                     : (in_dict || (src_lo >= 8 && src_lo + (i32)ml + 4 <= w.near_lo)));
         const bool m_lane_ok = m_word_ok && ml <= MATCH_SHORT && off >= ml;
 #if ZXC_BALANCED
         const bool m_grp_ok = m_word_ok && !m_lane_ok && off >= ml; /* chunks of one item run side by side */
 #else
         const bool m_grp_ok = m_word_ok && !m_lane_ok && off >= 36;
 #endif
-        const u8* m_sp = near ? ring + si : out + src_lo;
+        const u8* m_sp = near ? ring + si : (src_lo < 0 ? dict + ((i32)dict_size + src_lo) : out + src_lo);
+#if ZXC_PF_FAR
+        if (act && !near && src_lo >= 0) prefetch_l1(m_sp); /* far sources start travelling while the literals are copied */
+#endif
         const bool l_word_ok = (out_start & mask) + ll + 4 <= RING_BYTES;
 
         /* ---- dependency masks ---- */
@@ -1007,23 +1028,21 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
         }
         /* ---- pass loop ---- */
         u32 pending = __ballot_sync(FULL, act);
+        ZXC_STAT(0, 1);            /* batches */
+        ZXC_STAT(1, m);            /* sequences */
         bool lit_pass = true;
 #pragma unroll 1
         for (;;) {
             bool ready, lok, gok;
             u32 it_d, it_n;
             const u8* it_sp;
-            bool m0 = false; /* pass 0, lane without literals: its match goes now if the source lies before this batch */
             if (lit_pass) {
-#if ZXC_MERGE_PASS0
-                m0 = act && ll == 0 && src_end <= (i32)O;
-#endif
-                ready = (act && ll > 0) || m0;
-                it_d = m0 ? mdst : out_start;
-                it_n = m0 ? ml : ll;
-                it_sp = m0 ? m_sp : lit + lit_start;
-                lok = m0 ? m_lane_ok : (l_word_ok && ll <= LIT_SHORT);
-                gok = m0 ? m_grp_ok : (l_word_ok && ll > LIT_SHORT);
+                ready = act && ll > 0;
+                it_d = out_start;
+                it_n = ll;
+                it_sp = lit + lit_start;
+                lok = l_word_ok && ll <= LIT_SHORT;
+                gok = l_word_ok && ll > LIT_SHORT;
             } else {
                 ready = ((pending >> lane) & 1u) && (pending & depmask) == 0;
                 it_d = mdst;
@@ -1038,6 +1057,12 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
             lane_copy_words<ZXC_NW>(ring, it_d, it_sp, it_n, ready && lok);
 #endif
             const u32 m_grp = __ballot_sync(FULL, ready && gok);
+            ZXC_STAT(2, 1);                                           /* passes */
+            ZXC_STAT(3, __popc(__ballot_sync(FULL, ready && lok)));   /* per-lane items */
+            ZXC_STAT(4, __popc(m_grp));                               /* long items */
+            ZXC_STAT(5, m_grp != 0);                                  /* long-copy calls */
+            ZXC_STAT(6, __popc(__ballot_sync(FULL, ready && !lok && !gok))); /* slow items */
+            ZXC_STAT(7, __ballot_sync(FULL, ready && lok) != 0);      /* passes with a per-lane item */
 #if ZXC_BALANCED
             if (m_grp) balanced_copy_words(ring_s, m_grp, it_d, it_sp, it_n, lane);
 #else
@@ -1048,22 +1073,20 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
                 const int j = __ffs(m_slow) - 1;
                 m_slow &= m_slow - 1;
                 const u32 d = __shfl_sync(FULL, it_d, j), n = __shfl_sync(FULL, it_n, j);
-                const bool as_lit = lit_pass && !m0;
-                const u32 aux = __shfl_sync(FULL, (as_lit ? lit_start : off) | (as_lit ? 0x80000000u : 0u), j);
-                if (aux >> 31) {
-                    for (u32 k = lane; k < n; k += 32) ring[(d + k) & mask] = lit[(aux & 0x7FFFFFFFu) + k];
+                const u32 aux = __shfl_sync(FULL, lit_pass ? lit_start : off, j);
+#if ZXC_COLD_CALLS
+                slow_item(ring, out, dict, dict_size, w.near_lo, lit_pass ? lit : (const u8*)0, d, n, aux, lane);
+#else
+                if (lit_pass) {
+                    for (u32 k = lane; k < n; k += 32) ring[(d + k) & mask] = lit[aux + k];
                 } else {
                     warp_match_to_ring(w, d, aux, n, lane);
                 }
+#endif
             }
             __syncwarp();
-#if ZXC_MERGE_PASS0
-            pending &= ~__ballot_sync(FULL, lit_pass ? m0 : ready);
-            lit_pass = false;
-#else
             if (lit_pass) lit_pass = false;
             else pending &= ~__ballot_sync(FULL, ready);
-#endif
             if (!pending) break;
         }
 

@@ -657,8 +657,11 @@ static int launch_decode(const void* d_src, void* d_dst, const zxc_b200_job_t* d
         if (units_mode == 1) P.flags |= FLAG_UNITS_ON;
         if (units_mode == 0) P.flags |= FLAG_UNITS_OFF;
     }
-    /* the output-centric body where it measured faster: dictionary decodes of small blocks */
-    const bool units = (P.flags & FLAG_UNITS_ON) || (!(P.flags & FLAG_UNITS_OFF) && P.dict_size != 0 && block_size <= 16384u);
+    /* The output-centric body (zxc_decode_units.cuh) was the faster one for dictionary decodes of small blocks while the
+     * sequence-centric body copied dictionary sources byte by byte (298 vs 152 GB/s on 4 KiB records).  Since that body
+     * reads them as ordinary global sources and copies long items as balanced chunks it wins there too (369 vs 321 GB/s,
+     * DESIGN.md), so the unit walk runs only on request (ZXC_B200_UNITS=1). */
+    const bool units = (P.flags & FLAG_UNITS_ON) != 0;
     P.block_cap = block_size;
     P.defer_list = NULL;
     P.defer_count = NULL;
