@@ -14,9 +14,19 @@
 extern "C" { uint64_t simt_stat[32]; }
 #define ZXC_STAT(i, v) do { const uint64_t zv_ = (uint64_t)(v); if (simt::g_warp->current == 0) simt_stat[i] += zv_; } while (0)
 
-#include "zxc_decode.cuh"
+#include <stdio.h>
+uint32_t simt_bar_issued[64], simt_bar_waited[64];
+uint32_t simt_bar_base;
+void simt_stage_fail(const char* what) {
+    fprintf(stderr, "simt stage check failed: %s\n", what);
+    abort();
+}
 
-alignas(16) u8 smem[WARPS_PER_CTA * RING_BYTES];
+#include "zxc_decode.cuh"
+SimtStore simt_stores[64];
+u32 simt_n_stores;
+
+alignas(16) u8 smem[DECODE_SMEM_BYTES];
 
 namespace {
 const u32 PAD = 256;
@@ -55,11 +65,19 @@ extern "C" uint64_t simt_decode_blocks(const u8* src, uint64_t src_size, u8* dst
         u8* scr = P.scratch + 256; /* the lead-in zxc_decode_kernel leaves */
         u8* ring = smem;
         auto body = [&](unsigned lane) {
+#if ZXC_STAGE
+            simt_bar_base = smem_addr(ring) + RING_BYTES + ST_OFF_BAR;
+            st_init(smem_addr(ring) + RING_BYTES, lane);
+#endif
             const int r = units ? decode_job<true>(P, job, scr, ring, lane) : decode_job<false>(P, job, scr, ring, lane);
+            flush_wait(lane);
             __syncwarp();
             if (lane == 0) status[j] = r;
         };
         rendezvous += simt::run_warp(body, 0, 0, CTA_THREADS, seed ? seed + j : 0);
+        if (simt_n_stores) simt_stage_fail("a bulk store was still in flight when the warp finished");
+        for (int b = 0; b < 64; b++)
+            if (simt_bar_issued[b] != simt_bar_waited[b]) simt_stage_fail("a bulk copy was still in flight when the block ended");
     }
     int bad = 0;
     for (u32 k = 0; k < PAD; k++) bad += (out[k] != 0x5A) + (out[PAD + dst_size + k] != 0x5A);

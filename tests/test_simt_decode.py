@@ -92,3 +92,23 @@ def test_kernel_source_damaged_blocks_fail_like_the_reference(prod, ref):
                     assert room.get(bad[0], bad[0]) == room.get(r_ref, r_ref), (pos, z.ERR.get(bad[0], bad[0]), z.ERR.get(r_ref, r_ref))
             checked += 1
         assert checked >= 40
+
+
+@pytest.mark.skipif(bool(os.environ.get("ZXC_SIMT_SO")), reason="already running a variant build")
+def test_kernel_source_with_bulk_copy_staging():
+    """The opt-in TMA flavour of the kernel (token / offset / literal sections staged through shared memory by
+    cp.async.bulk, ring flushed by bulk stores: -DZXC_STAGE=1 -DZXC_STAGE_LIT=1 -DZXC_BULK_FLUSH=1) through the same
+    tests.  The emulator performs a bulk load when it is issued and a bulk store only when it is waited for, and keeps
+    the mbarriers' books: one copy in flight per barrier, every wait on the parity it names, nothing in flight at
+    the end of a block."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = os.path.join(here, "simt", "libzxc_simt_decode_staged.so")
+    r = subprocess.run(["make", "-s", "SO=" + so, "EXTRA=-DZXC_STAGE=1 -DZXC_STAGE_LIT=1 -DZXC_BULK_FLUSH=1"],
+                       cwd=os.path.join(here, "simt"), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    env = dict(os.environ, ZXC_SIMT_SO=so)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-p", "no:cacheprovider"],
+                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-2000:]

@@ -42,7 +42,6 @@ typedef int32_t i32;
 #define RING_BYTES 4096u          /* per-warp output ring (power of two, multiple of 512) */
 #endif
 #define RING_LIMIT (RING_BYTES - 576u) /* largest output span one batch may add */
-#define DECODE_SMEM_BYTES (WARPS_PER_CTA * RING_BYTES)
 #ifndef CTAS_PER_SM
 #define CTAS_PER_SM 7u            /* register-limited (72 regs x 128 threads); 112 KB of rings, rest is L1 */
 #endif
@@ -121,6 +120,10 @@ template <int OFF> static inline void sts32(u32 a, u32 v) { memcpy(smem + a + OF
 template <int OFF> static inline void sts16(u32 a, u32 v) { const unsigned short h = (unsigned short)v; memcpy(smem + a + OFF, &h, 2); }
 template <int OFF> static inline void sts8(u32 a, u32 v) { smem[a + OFF] = (u8)v; }
 #endif
+
+#include "zxc_decode_stage.cuh"
+#define WARP_SMEM_BYTES (RING_BYTES + STAGE_BYTES) /* a warp's output ring, its staging area right behind */
+#define DECODE_SMEM_BYTES (WARPS_PER_CTA * WARP_SMEM_BYTES)
 
 #include "zxc_huffman.cuh"
 
@@ -417,6 +420,23 @@ __device__ __forceinline__ void ring_flush(const Window& w, u32& F, u32 target, 
             if (p < head_end) w.out[p] = w.ring[p & mask];
             F = head_end;
         }
+#if ZXC_BULK_FLUSH
+        /* every whole 16-byte unit by the bulk-copy engine: one or two copies (the ring wraps) issued by lane 0; the
+         * warp's writes to the ring are ordered before them by the caller's __syncwarp() and the proxy fence.  The
+         * copies complete under flush_wait(), which the caller runs before the ring is written or the flushed output
+         * is read again. */
+        const u32 nb = (target - F) & ~15u;
+        if (nb) {
+            if (lane == 0) {
+                const u32 r = F & mask, first = min(nb, RING_BYTES - r);
+                st_store_fence();
+                st_store(w.out + F, smem_addr(w.ring) + r, first);
+                if (first < nb) st_store(w.out + F + first, smem_addr(w.ring), nb - first);
+                st_store_commit();
+            }
+            F += nb;
+        }
+#else
         while (target - F >= 512u) {
             const uint4 v = *reinterpret_cast<const uint4*>(w.ring + ((F + 16u * lane) & mask));
             *reinterpret_cast<uint4*>(w.out + F + 16u * lane) = v;
@@ -428,9 +448,20 @@ __device__ __forceinline__ void ring_flush(const Window& w, u32& F, u32 target, 
             *reinterpret_cast<uint4*>(w.out + F + 16u * lane) = v;
         }
         F += units << 4;
+#endif
     }
     for (u32 p = F + lane; p < target; p += 32) w.out[p] = w.ring[p & mask];
     F = target;
+}
+
+/* the bulk copies of ring_flush have read the ring and their output is visible to the warp */
+__device__ __forceinline__ void flush_wait(u32 lane) {
+#if ZXC_BULK_FLUSH
+    if (lane == 0) st_store_wait();
+    __syncwarp();
+#else
+    (void)lane;
+#endif
 }
 
 /* whole-warp copy of n bytes from a generic source pointer into the ring at dpos, 128 bytes per
@@ -872,20 +903,84 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
         __syncwarp();
     }
 
+#if ZXC_STAGE
+    /* the token / offset sections come through shared memory (zxc_decode_stage.cuh); Huffman-decoded tokens sit in the
+     * scratch and are read from there */
+    const u32 tok_w = ghi ? 4u : 1u, off_w = enc_off ? 1u : 2u;
+    const u32 tx0 = (u32)(reinterpret_cast<uintptr_t>(tok) & 15u), ox0 = (u32)(reinterpret_cast<uintptr_t>(offs) & 15u);
+    const u32 stage_s = smem_addr(ring) + RING_BYTES;
+    {
+        SeqStream t = st_tok(stage_s), o = st_off(stage_s);
+        const u32 ct = t.open(tok, tok_w * n_seq, pay + comp, tok >= pay && tok < pay + comp, tx0 + tok_w * min(32u, n_seq), lane);
+        const u32 co = o.open(offs, ghi ? 0u : off_w * n_seq, pay + comp, !ghi, ox0 + off_w * min(32u, n_seq), lane);
+        sts32<0>(stage_s + ST_OFF_STATE, ct); /* every lane writes the same words and later reads what it wrote */
+        sts32<4>(stage_s + ST_OFF_STATE, co);
+#if ZXC_STAGE_LIT
+        lit_open(stage_s, lit, n_lit_avail, pay + comp, lit >= pay && lit < pay + comp); /* raw literals only */
+#endif
+    }
+#if ZXC_STAGE_LIT
+#define ST_LIT_CLOSE() lit_close(stage_s)
+#else
+#define ST_LIT_CLOSE() do { } while (0)
+#endif
+#define ST_CLOSE()                                                                                   \
+    do {                                                                                             \
+        st_tok(stage_s).close(tx0 + tok_w * base, tx0 + tok_w * min(base + 32u, n_seq));             \
+        st_off(stage_s).close(ox0 + off_w * base, ox0 + off_w * min(base + 32u, n_seq));             \
+        ST_LIT_CLOSE();                                                                              \
+    } while (0)
+#else
+#define ST_CLOSE() do { } while (0)
+#define ST_LIT_CLOSE() do { } while (0)
+#endif
+
     u32 base = 0;
     while (base < n_seq) {
         /* ---- unpack tokens and offsets ---- */
         const u32 i = base + lane;
         const bool valid = i < n_seq;
         u32 ll = 0, ml = 0, off = 1;
+#if ZXC_STAGE
+        const u32 i_end = min(base + 32u, n_seq);
+        const SeqStream st_t = st_tok(stage_s), st_o = st_off(stage_s);
+        const bool t_st = st_t.staged(tx0 + tok_w * i_end), o_st = st_o.staged(ox0 + off_w * i_end);
+#endif
         if (valid) {
             u32 a, b = 0;
+#if ZXC_STAGE
+            if (!ghi) {
+                a = t_st ? lds8(st_t.ring_s + ((tx0 + i) & (ST_RING - 1u))) : (u32)tok[i];
+                if (!o_st) {
+                    b = enc_off ? (u32)offs[i] : ld16(offs + 2 * (size_t)i);
+                } else if (enc_off) {
+                    b = lds8(st_o.ring_s + ((ox0 + i) & (ST_RING - 1u)));
+                } else {
+                    const u32 x = ox0 + 2u * i;
+                    b = (ox0 & 1u) ? (lds8(st_o.ring_s + (x & (ST_RING - 1u))) |
+                                      (lds8(st_o.ring_s + ((x + 1u) & (ST_RING - 1u))) << 8))
+                                   : lds16(st_o.ring_s + (x & (ST_RING - 1u)));
+                }
+            } else if (t_st) {
+                const u32 x = tx0 + 4u * i;
+                if (tx0 & 3u) {
+                    a = lds8(st_t.ring_s + (x & (ST_RING - 1u))) | (lds8(st_t.ring_s + ((x + 1u) & (ST_RING - 1u))) << 8) |
+                        (lds8(st_t.ring_s + ((x + 2u) & (ST_RING - 1u))) << 16) |
+                        (lds8(st_t.ring_s + ((x + 3u) & (ST_RING - 1u))) << 24);
+                } else {
+                    a = lds32(st_t.ring_s + (x & (ST_RING - 1u)));
+                }
+            } else {
+                a = ld32(tok + 4 * (size_t)i);
+            }
+#else
             if (!ghi) {
                 a = tok[i];
                 b = enc_off ? (u32)offs[i] : ld16(offs + 2 * (size_t)i);
             } else {
                 a = ld32(tok + 4 * (size_t)i);
             }
+#endif
             if (!ghi) {
                 ll = a >> 4;
                 ml = a & 15;
@@ -935,11 +1030,18 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
             /* ---- giant sequence (lane 0): bypass the ring, global -> global ---- */
             const u32 g_ll = __shfl_sync(FULL, ll, 0), g_ml = __shfl_sync(FULL, ml, 0),
                       g_off = __shfl_sync(FULL, off, 0);
-            if (L + g_ll > n_lit_avail || (u64)O + g_ll + g_ml > cap) return ZXC_ERROR_OVERFLOW;
-            if (O + g_ll + dict_size < g_off) return ZXC_ERROR_BAD_OFFSET;
+            if (L + g_ll > n_lit_avail || (u64)O + g_ll + g_ml > cap) {
+                ST_CLOSE();
+                return ZXC_ERROR_OVERFLOW;
+            }
+            if (O + g_ll + dict_size < g_off) {
+                ST_CLOSE();
+                return ZXC_ERROR_BAD_OFFSET;
+            }
             __syncwarp();
             ring_flush(w, F, O, lane, al16);
             __syncwarp();
+            flush_wait(lane);
             warp_copy(out + O, lit + L, g_ll, lane);
             __syncwarp();
             warp_match_global(w, O + g_ll, g_off, g_ml, lane);
@@ -955,6 +1057,12 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
             ord_base += q;
             if (!use_vals)
                 for (u32 s = 0; s < q; s++) epos = varint_advance(ext, epos, ext_end); /* rare: re-walk */
+#if ZXC_STAGE
+            st_t.step(tok, tx0 + tok_w * base, tx0 + tok_w * i_end, tx0 + tok_w * (base + 1u),
+                        tx0 + tok_w * min(base + 33u, n_seq), lane);
+            st_o.step(offs, ox0 + off_w * base, ox0 + off_w * i_end, ox0 + off_w * (base + 1u),
+                        ox0 + off_w * min(base + 33u, n_seq), lane);
+#endif
             base += 1;
             continue;
         }
@@ -966,9 +1074,14 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
         const u32 m_err = __ballot_sync(FULL, ovf || bad);
         if (m_err) {
             const int code = ovf ? ZXC_ERROR_OVERFLOW : ZXC_ERROR_BAD_OFFSET;
+            ST_CLOSE();
             return __shfl_sync(FULL, code, __ffs(m_err) - 1);
         }
         const u32 T = __shfl_sync(FULL, s_tot, m - 1), TL = __shfl_sync(FULL, s_ll, m - 1);
+#if ZXC_STAGE && ZXC_STAGE_LIT
+        const u32 lx0 = (u32)(reinterpret_cast<uintptr_t>(lit) & 15u);
+        const LitWindow lw = lit_need(stage_s, lit, lx0 + L, lx0 + L + TL, lane);
+#endif
 #if ZXC_PF_STREAM
         /* the three input streams advance linearly: ask for the sectors the next batches will read while this one copies */
         if (lane < 4) {
@@ -983,6 +1096,7 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
             w.near_lo = a > (i32)ring_lo ? a : (i32)ring_lo;
         }
 
+        flush_wait(lane); /* the previous flush has left the ring and reached the output */
         /* ---- copy passes: pass 0 = every literal run (independent of all matches), then match
          * rounds: a match is ready once its source ends below the lowest pending match destination.
          * One body serves all passes so the hot loop stays inside the instruction cache. ---- */
@@ -1082,6 +1196,14 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
                 it_d = out_start;
                 it_n = ll;
                 it_sp = lit + lit_start;
+#if ZXC_STAGE && ZXC_STAGE_LIT
+                {
+                    const u8* sp_s = lit_ptr(lw, lx0 + lit_start, ll);
+                    if (sp_s) it_sp = sp_s;
+                    ZXC_STAT(13, __popc(__ballot_sync(FULL, ready && sp_s != 0))); /* literal runs read from the ring */
+                    ZXC_STAT(14, __popc(__ballot_sync(FULL, ready)));
+                }
+#endif
                 lok = l_word_ok && ll <= LIT_SHORT;
                 gok = l_word_ok && ll > LIT_SHORT;
             } else {
@@ -1166,6 +1288,13 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
         ring_flush(w, F, O & ~511u, lane, al16);
         __syncwarp();
 
+#if ZXC_STAGE
+        {   /* the next batch's tokens and offsets: issue what the rings have room for, wait for what it reads */
+            const u32 nb = base + (m < nvalid ? m : 32u), ne = min(nb + 32u, n_seq);
+            st_t.step(tok, tx0 + tok_w * base, tx0 + tok_w * i_end, tx0 + tok_w * nb, tx0 + tok_w * ne, lane);
+            st_o.step(offs, ox0 + off_w * base, ox0 + off_w * i_end, ox0 + off_w * nb, ox0 + off_w * ne, lane);
+        }
+#endif
         if (m < nvalid) {
             const u32 below = (1u << m) - 1u;
             const u32 q = __popc(m_ll & below) + __popc(m_ml & below);
@@ -1181,10 +1310,12 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
     }
 
     /* trailing literals (zxc_decompress.c:1198-1206) */
+    ST_LIT_CLOSE();
     const u32 rem = n_lit_avail - L;
     if (rem > cap - O) return ZXC_ERROR_OVERFLOW;
     ring_flush(w, F, O, lane, al16);
     __syncwarp();
+    flush_wait(lane);
     warp_copy(out + O, lit + L, rem, lane);
     return (int)(O + rem);
 }
@@ -1230,7 +1361,10 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) zxc_decode_kernel(co
     const u32 wic = threadIdx.x >> 5;
     const u32 gwarp = blockIdx.x * WARPS_PER_CTA + wic;
     u8* scratch = P.scratch + (size_t)gwarp * P.scratch_stride + 256; /* lead-in: word loads may start below */
-    u8* ring = smem + (size_t)wic * RING_BYTES;
+    u8* ring = smem + (size_t)wic * WARP_SMEM_BYTES;
+#if ZXC_STAGE
+    st_init(smem_addr(ring) + RING_BYTES, lane);
+#endif
     if (DEFERRED) {
         const u32 n_def = *P.defer_count;
         if (n_def <= P.defer_cap) { /* the listed jobs, one per claim */
@@ -1242,6 +1376,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) zxc_decode_kernel(co
                 const u32 j = P.defer_list[k];
                 const zxc_b200_job_t job = P.jobs[j];
                 const int r = decode_job<UNITS>(P, job, scratch, ring, lane);
+                flush_wait(lane); /* nothing of this block is still on its way out of the ring */
                 __syncwarp();
                 if (lane == 0) P.status[j] = r;
             }
@@ -1260,6 +1395,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) zxc_decode_kernel(co
                 m &= m - 1;
                 const zxc_b200_job_t job = P.jobs[j];
                 const int r = decode_job<UNITS>(P, job, scratch, ring, lane);
+                flush_wait(lane); /* nothing of this block is still on its way out of the ring */
                 __syncwarp();
                 if (lane == 0) P.status[j] = r;
             }
@@ -1273,6 +1409,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) zxc_decode_kernel(co
         if (j >= P.n_jobs) break;
         const zxc_b200_job_t job = P.jobs[j];
         const int r = decode_job<UNITS>(P, job, scratch, ring, lane);
+                flush_wait(lane); /* nothing of this block is still on its way out of the ring */
         __syncwarp();
         if (lane == 0) P.status[j] = r;
     }

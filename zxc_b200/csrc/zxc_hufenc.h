@@ -158,178 +158,181 @@ ZXH int zxh_build_code_lengths(const uint32_t* freq, uint8_t* code_len, int max_
     return 0;
 }
 
-/* ---- nudge ---------------------------------------------------------------------------------- */
-typedef struct { uint64_t bits, touches; } zxh_cost_t;
+/* ---- cost model of a code shape (what zxc_huffman.c:343-431 prices) ---------------------------------
+ * A canonical code hands out its code space from the left, shorter codes first.  At length l the next free
+ * codeword has index `at` counted in codewords of that length (at = 0 at length 1; at' = 2 (at + c) one level down
+ * after c leaves), so the c leaves of one length are the index interval [at, at + c).  The decoder resolves an
+ * aligned block of 2^D of them with one table step, and the interval splits in exactly one way into maximal aligned
+ * blocks.  They are found here from the two ends: going up, every set bit of the left end whose block still fits is
+ * peeled off; what remains is shorter than the alignment reached and splits by the set bits of its length, largest
+ * first.  (The reference walks the same blocks left to right; integer sums do not care.)  Costs are two sums over
+ * the symbol masses: code bits, and decoder work = mass x (steps to resolve a symbol of that block).
+ * g > 0 is the grouped view of the DP: an item is a group of 2^g symbols, its level lc sits g above the leaves. */
+typedef struct { uint64_t bits, work; } zxh_cost_t;
 
-ZXH int zxh_classes(const uint8_t* code_len, uint32_t* blc) {
-    int n = 0;
-    for (int l = 0; l <= ZXH_LU; l++) blc[l] = 0;
-    for (int s = 0; s < ZXH_NSYM; s++) {
-        if (code_len[s]) {
-            blc[code_len[s]]++;
-            n++;
+/* steps for a symbol of length len inside a flat block of depth D: walk len - D levels, then one lookup -- wide
+ * lookups (D > 6) are charged extra */
+ZXH uint64_t zxh_block_weight(int len, int D) { return (uint64_t)(len + 1 - D + (D > ZXH_FLAT_SIMD_MAX ? ZXH_DEEP_FLAT_PENALTY : 0)); }
+
+/* add c items of level lc (length lc + g) that start at index `at`; their masses are pf[first .. first + c] */
+ZXH void zxh_cost_add(zxh_cost_t* acc, int lc, int g, uint32_t at, uint32_t c, const uint64_t* pf, uint32_t first) {
+    if (!c) return;
+    const int len = lc + g;
+    acc->bits += (uint64_t)len * (pf[first + c] - pf[first]);
+    uint32_t lo = at, i = first;
+    const uint32_t hi = at + c;
+    int d = 0;
+    for (; (1u << d) <= hi - lo; d++) { /* lo is a multiple of 2^d here */
+        const uint32_t sz = 1u << d;
+        if (lo & sz) {
+            acc->work += (pf[i + sz] - pf[i]) * zxh_block_weight(len, d + g);
+            lo += sz;
+            i += sz;
         }
     }
+    while (d-- > 0) { /* hi - lo < 2^(d+1) and lo is aligned that far: the rest by the bits of its length */
+        const uint32_t sz = 1u << d;
+        if ((hi - lo) & sz) {
+            acc->work += (pf[i + sz] - pf[i]) * zxh_block_weight(len, d + g);
+            lo += sz;
+            i += sz;
+        }
+    }
+}
+
+ZXH uint64_t zxh_j(const zxh_cost_t* c) { return 256u * c->bits + (uint64_t)ZXH_LAMBDA_Q8 * c->work; }
+
+/* cost of a whole shape: cnt[l] leaves of length l, masses in the order the lengths are handed out */
+ZXH void zxh_shape_cost(const uint32_t* cnt, const uint64_t* pf, zxh_cost_t* out) {
+    out->bits = out->work = 0;
+    uint32_t at = 0, first = 0;
+    int deepest = 0;
+    for (int l = 1; l <= ZXH_LU; l++) {
+        zxh_cost_add(out, l, 0, at, cnt[l], pf, first);
+        if (cnt[l]) deepest = l;
+        first += cnt[l];
+        at = 2 * (at + cnt[l]);
+    }
+    out->work += (uint64_t)ZXH_LEVEL_COST * (uint64_t)(deepest + 1);
+}
+
+/* cost of a set of code lengths: leaves per length, masses laid out by (length, symbol) */
+ZXH int zxh_lengths_cost(const uint8_t* code_len, const uint32_t* freq, zxh_work_t* W, uint32_t* cnt, zxh_cost_t* out) {
+    uint32_t next[ZXH_LU + 2];
+    int n = 0;
+    for (int l = 0; l <= ZXH_LU; l++) cnt[l] = 0;
+    for (int s = 0; s < ZXH_NSYM; s++) cnt[code_len[s]]++;
+    n = ZXH_NSYM - (int)cnt[0];
+    cnt[0] = 0;
+    next[1] = 0;
+    for (int l = 1; l <= ZXH_LU; l++) next[l + 1] = next[l] + cnt[l];
+    for (int s = 0; s < ZXH_NSYM; s++)
+        if (code_len[s]) W->val[next[code_len[s]]++] = freq[s];
+    W->pf[0] = 0;
+    for (int i = 0; i < n; i++) W->pf[i + 1] = W->pf[i] + W->val[i];
+    zxh_shape_cost(cnt, W->pf, out);
     return n;
 }
 
-/* prefix masses of the frequencies laid out in canonical (length, symbol) order */
-ZXH void zxh_prefix_masses(const uint8_t* code_len, const uint32_t* freq, const uint32_t* blc, uint64_t* pf, uint32_t* val) {
-    uint32_t pos[ZXH_LU + 1];
-    uint32_t acc = 0;
-    for (int l = 1; l <= ZXH_LU; l++) {
-        pos[l] = acc;
-        acc += blc[l];
-    }
-    for (int s = 0; s < ZXH_NSYM; s++)
-        if (code_len[s]) val[pos[code_len[s]]++] = freq[s];
-    pf[0] = 0;
-    for (uint32_t i = 0; i < acc; i++) pf[i + 1] = pf[i] + val[i];
+/* How many of the `left` remaining leaves can take length l when `open` codewords of that length are free and no
+ * code may be longer than cap.  If they all fit, or this is the last length, they all go here.  Otherwise c of
+ * them here leaves left - c for the 2 (open - c) codewords one level down: that needs at least one inner node
+ * (c <= open - 1), must not strand code space (left - c >= 2 (open - c), i.e. c >= 2 open - left) and must still fit
+ * at the cap (left - c <= (open - c) 2^(cap - l)).  `want` is pulled into that range. */
+ZXH uint32_t zxh_fit(uint32_t want, uint32_t open, uint32_t left, int l, int cap) {
+    if (left <= open || l >= cap) return left;
+    const uint64_t room = (uint64_t)1 << (cap - l);
+    const uint64_t most = ((uint64_t)open * room - left) / (room - 1);
+    const uint32_t hi = most < open - 1 ? (uint32_t)most : open - 1;
+    const uint32_t lo = 2 * open > left ? 2 * open - left : 0;
+    return want < lo ? lo : (want > hi ? hi : want);
 }
 
-/* decode-work weight of one maximal aligned sub-tree of D levels whose leaves have length lr */
-ZXH int zxh_touch_weight(int lr, int D) {
-    if (D == 0) return lr + 1;
-    if (D == 1) return lr;
-    return (lr - D) + 1 + (D > ZXH_FLAT_SIMD_MAX ? ZXH_DEEP_FLAT_PENALTY : 0);
-}
-
-/* bits and decoder "touches" of a code given its per-length leaf counts and prefix masses */
-ZXH void zxh_eval(const uint32_t* blc, const uint64_t* pf, zxh_cost_t* out) {
-    uint64_t bits = 0, touches = 0;
-    int max_len = 0;
-    uint32_t S = 0, base = 0; /* code-space cursor in 2^-LU slots; first leaf of the current length */
-    for (int l = 1; l <= ZXH_LU; l++) {
-        if (!blc[l]) continue;
-        max_len = l;
-        bits += (uint64_t)l * (pf[base + blc[l]] - pf[base]);
-        const uint32_t w = 1u << (ZXH_LU - l);
-        const uint32_t end = S + blc[l] * w;
-        uint32_t x = S;
-        while (x < end) { /* split [S, end) into maximal aligned power-of-two spans */
-            const uint32_t wx = x ? (x & (0u - x)) : (1u << ZXH_LU);
-            const uint32_t wr = 1u << zxh_log2(end - x);
-            const uint32_t Wd = wx < wr ? wx : wr;
-            const int D = (int)zxh_log2(Wd) - (ZXH_LU - l);
-            const uint32_t i0 = base + ((x - S) >> (ZXH_LU - l));
-            const uint64_t mass = pf[i0 + (Wd >> (ZXH_LU - l))] - pf[i0];
-            touches += mass * (uint64_t)zxh_touch_weight(l, D);
-            x += Wd;
-        }
-        S = end;
-        base += blc[l];
-    }
-    touches += (uint64_t)ZXH_LEVEL_COST * (uint64_t)(max_len + 1);
-    out->bits = bits;
-    out->touches = touches;
-}
-
-ZXH uint64_t zxh_j(const zxh_cost_t* c) { return 256u * c->bits + (uint64_t)ZXH_LAMBDA_Q8 * c->touches; }
-
-/* how many of the n_rem remaining leaves may sit at level l when s slots are open there */
-ZXH uint32_t zxh_clamp(uint32_t want, uint32_t s, uint32_t n_rem, int l, int cap) {
-    if (n_rem <= s || l >= cap) return n_rem;
-    const uint64_t m = (uint64_t)1 << (cap - l);
-    const uint32_t lo = (2 * s > n_rem) ? 2 * s - n_rem : 0;
-    uint32_t hi = s - 1;
-    const uint64_t cap_hi = ((uint64_t)s * m - n_rem) / (m - 1);
-    if (cap_hi < hi) hi = (uint32_t)cap_hi;
-    const uint32_t c = want < lo ? lo : want;
-    return c > hi ? hi : c;
-}
-
-ZXH void zxh_complete(uint32_t* blc, int l, uint32_t s, uint32_t n_rem, const uint32_t* blc0, int cap) {
-    for (int j = l + 1; j <= cap && n_rem; j++) {
-        const uint32_t c = zxh_clamp(blc0[j], s, n_rem, j, cap);
-        blc[j] = c;
-        n_rem -= c;
-        s = 2 * (s - c);
-    }
-}
-
-/* greedy level-by-level choice of leaf counts, each level trying a handful of "flatter" shapes */
-ZXH void zxh_walk(const uint32_t* blc0, const uint64_t* pf_rank, int n, int cap, uint32_t* out_blc) {
-    for (int l = 0; l <= ZXH_LU; l++) out_blc[l] = 0;
-    uint32_t s = 2, n_rem = (uint32_t)n;
-    for (int l = 1; l <= cap && n_rem; l++) {
-        uint32_t cand_c[6];
-        int cand_flat[6];
-        int n_cand = 0;
-        const uint32_t c_base = zxh_clamp(blc0[l], s, n_rem, l, cap);
-        cand_c[n_cand] = c_base;
-        cand_flat[n_cand++] = 0;
-        if (c_base < n_rem) {
-            const uint32_t i_base = s - c_base;
-            const uint32_t i_dn = 1u << zxh_log2(i_base);
-            const uint32_t rest = i_base - i_dn;
-            const uint32_t shapes[3] = {i_dn, i_dn << 1, i_dn | (rest ? 1u << zxh_log2(rest) : 0u)};
-            for (int k = 0; k < 3; k++) {
-                const uint32_t want = s > shapes[k] ? s - shapes[k] : 0;
-                const uint32_t c = zxh_clamp(want, s, n_rem, l, cap);
-                int dup = 0;
-                for (int p = 0; p < n_cand; p++) dup |= (cand_c[p] == c);
-                if (!dup) {
-                    cand_c[n_cand] = c;
-                    cand_flat[n_cand++] = 0;
+/* Greedy reshaping, level by level (zxc_huffman.c:432-590): at each length try the baseline count and a few counts
+ * that leave a rounder number of inner nodes, finish each trial the baseline's way (or as one flat run), keep the
+ * cheapest.  The trials of one level share everything above it, so only the part from this level down is priced:
+ * the order of the totals is the order of these tails. */
+ZXH void zxh_walk(const uint32_t* want, const uint64_t* pf, int n, int cap, uint32_t* cnt) {
+    for (int l = 0; l <= ZXH_LU; l++) cnt[l] = 0;
+    uint32_t open = 2, left = (uint32_t)n, first = 0;
+    for (int l = 1; l <= cap && left; l++) {
+        uint32_t opt[5];
+        int run[5]; /* > 0: everything that is left goes run[] levels further down as one flat block */
+        int k = 0;
+        opt[0] = zxh_fit(want[l], open, left, l, cap);
+        run[k++] = 0;
+        if (opt[0] < left) {
+            /* inner nodes kept by the baseline, rounded down to a power of two, that doubled, or its two leading bits */
+            const uint32_t inner = open - opt[0];
+            const uint32_t top = 1u << zxh_log2(inner);
+            const uint32_t two = inner == top ? top : top | (1u << zxh_log2(inner - top));
+            for (int t = 0; t < 3; t++) {
+                const uint32_t keep = t == 0 ? top : (t == 1 ? 2 * top : two);
+                const uint32_t c = zxh_fit(open > keep ? open - keep : 0, open, left, l, cap);
+                int seen = 0;
+                for (int q = 0; q < k; q++) seen |= opt[q] == c;
+                if (!seen) {
+                    opt[k] = c;
+                    run[k++] = 0;
                 }
             }
-            for (int d = 1; d <= cap - l && n_cand < 6; d++) { /* finish exactly as one flat run d levels down */
-                const uint64_t den = ((uint64_t)1 << d) - 1;
-                const int64_t num = (int64_t)((uint64_t)s << d) - (int64_t)n_rem;
-                if (num < 0 || (uint64_t)num % den) continue;
-                const uint64_t c64 = (uint64_t)num / den;
-                if (c64 >= s || c64 >= n_rem) continue;
-                cand_c[n_cand] = (uint32_t)c64;
-                cand_flat[n_cand++] = d;
+            /* the shallowest flat finish: (open - c) 2^d codewords for exactly left - c leaves */
+            for (int d = 1; d <= cap - l; d++) {
+                const uint64_t span = ((uint64_t)open << d), per = ((uint64_t)1 << d) - 1;
+                if (span < left || (span - left) % per) continue;
+                const uint64_t c = (span - left) / per;
+                if (c >= open || c >= left) continue;
+                opt[k] = (uint32_t)c;
+                run[k++] = d;
                 break;
             }
         }
-        uint64_t best_j = ZXH_U64MAX;
-        uint32_t best_c = c_base;
-        for (int k = 0; k < n_cand; k++) {
-            uint32_t tmp[ZXH_LU + 1];
-            for (int q = 0; q <= ZXH_LU; q++) tmp[q] = out_blc[q];
-            tmp[l] = cand_c[k];
-            const uint32_t rem = n_rem - cand_c[k];
-            if (rem) {
-                if (cand_flat[k]) tmp[l + cand_flat[k]] = rem;
-                else zxh_complete(tmp, l, 2 * (s - cand_c[k]), rem, blc0, cap);
+        uint64_t best = ZXH_U64MAX;
+        uint32_t pick = opt[0];
+        for (int q = 0; q < k; q++) {
+            zxh_cost_t tail;
+            tail.bits = tail.work = 0;
+            uint32_t at = (1u << l) - open, o = open, r = left, f = first;
+            int lv = l, deepest = l;
+            uint32_t c = opt[q];
+            for (;;) {
+                zxh_cost_add(&tail, lv, 0, at, c, pf, f);
+                if (c) deepest = lv;
+                r -= c;
+                if (!r) break;
+                f += c;
+                if (run[q]) { /* one flat block run[q] levels down takes the rest */
+                    at = (at + c) << run[q];
+                    lv += run[q];
+                    c = r;
+                    continue;
+                }
+                o = 2 * (o - c);
+                at = 2 * (at + c);
+                lv++;
+                c = zxh_fit(want[lv], o, r, lv, cap);
             }
-            zxh_cost_t cc;
-            zxh_eval(tmp, pf_rank, &cc);
-            const uint64_t j = zxh_j(&cc);
-            if (j < best_j) {
-                best_j = j;
-                best_c = cand_c[k];
+            tail.work += (uint64_t)ZXH_LEVEL_COST * (uint64_t)(deepest + 1);
+            const uint64_t j = zxh_j(&tail);
+            if (j < best) {
+                best = j;
+                pick = opt[q];
             }
         }
-        out_blc[l] = best_c;
-        n_rem -= best_c;
-        s = 2 * (s - best_c);
+        cnt[l] = pick;
+        first += pick;
+        left -= pick;
+        open = 2 * (open - pick);
     }
 }
 
-/* cost of c groups placed at grouped level lc when s slots are open and k groups are already placed */
+/* cost of c groups placed at grouped level lc when s slots are open there and k groups are already placed */
 ZXH uint64_t zxh_run_cost(int lu, int lc, int g_log2, uint32_t s, uint32_t c, const uint64_t* pfg, uint32_t k) {
-    if (!c) return 0;
-    const int lr = lc + g_log2;
-    const uint32_t w = 1u << (lu - lc);
-    const uint32_t S = (1u << lu) - s * w;
-    const uint32_t end = S + c * w;
-    const uint64_t bits = (uint64_t)lr * (pfg[k + c] - pfg[k]);
-    uint64_t touches = 0;
-    uint32_t x = S;
-    while (x < end) {
-        const uint32_t wx = x ? (x & (0u - x)) : (1u << lu);
-        const uint32_t wr = 1u << zxh_log2(end - x);
-        const uint32_t Wd = wx < wr ? wx : wr;
-        const int d = (int)zxh_log2(Wd >> (lu - lc)) + g_log2;
-        const uint32_t i0 = k + ((x - S) >> (lu - lc));
-        const uint64_t mass = pfg[i0 + (Wd >> (lu - lc))] - pfg[i0];
-        touches += mass * (uint64_t)zxh_touch_weight(lr, d);
-        x += Wd;
-    }
-    return 256u * bits + (uint64_t)ZXH_LAMBDA_Q8 * touches;
+    zxh_cost_t r;
+    (void)lu;
+    r.bits = r.work = 0;
+    zxh_cost_add(&r, lc, g_log2, (1u << lc) - s, c, pfg, k);
+    return zxh_j(&r);
 }
 
 /* ---- grouped DP over (groups placed k, open slots s) per level (zxc_huffman.c:682-773) ------------
@@ -433,7 +436,8 @@ ZXH int zxh_dp_solve(const uint64_t* pfg, int m, int cap_c, int lu, int g_log2, 
     return zxh_dp_backtrack(W->arrive, m, &B, out_cblc);
 }
 
-/* The nudge in three steps so that the grouped DP in the middle can run warp-wide on the device:
+/* The nudge (zxc_huffman.c:803-945) in three steps so that the grouped DP in the middle can run warp-wide on the
+ * device:
  *   zxh_nudge_begin  baseline cost, rank order, the walk and reduced-cap candidates, DP inputs
  *   (DP)             zxh_dp_solve here; zxh_dp_pull / zxh_dp_finish spread over lanes on the device
  *   zxh_nudge_end    DP candidate -> lengths, guard rails, adoption */
@@ -442,71 +446,68 @@ typedef struct {
     zxh_cost_t c0;
 } zxh_nudge_t;
 
+/* Lengths from a shape: ranks are served in order, cnt[lv] items of 2^g_log2 ranks each get length lv + g_log2.
+ * Ranks past the alphabet (the DP pads its last group) fall on absent symbols, lowest first. */
+ZXH void zxh_lengths_from_shape(const uint32_t* cnt, int levels, int g_log2, int n, const uint32_t* freq, const int16_t* order,
+                                uint8_t* cl) {
+    for (int s = 0; s < ZXH_NSYM; s++) cl[s] = 0;
+    int r = 0, spare = 0;
+    for (int lv = 1; lv <= levels; lv++) {
+        const int stop = r + ((int)cnt[lv] << g_log2);
+        for (; r < stop; r++) {
+            if (r < n) {
+                cl[order[r]] = (uint8_t)(lv + g_log2);
+            } else { /* a padding rank: the next symbol that does not occur */
+                while (spare < ZXH_NSYM && (freq[spare] != 0 || cl[spare] != 0)) spare++;
+                if (spare < ZXH_NSYM) cl[spare] = (uint8_t)(lv + g_log2);
+            }
+        }
+    }
+}
+
 /* 0: alphabet too small to reshape (code_len stays); 1: continue with the DP (if S->do_dp) and _end */
 ZXH int zxh_nudge_begin(const uint32_t* freq, const uint8_t* code_len, int max_code_len, zxh_work_t* W, zxh_nudge_t* S) {
-    uint32_t blc0[ZXH_LU + 1];
-    const int n = zxh_classes(code_len, blc0);
-    S->n = n;
-    S->n_cand = 0;
-    S->do_dp = 0;
-    if (n < 4) return 0;
-    zxh_prefix_masses(code_len, freq, blc0, W->pf, W->val);
-    zxh_eval(blc0, W->pf, &S->c0);
+    uint32_t base[ZXH_LU + 1];
+    S->n_cand = S->do_dp = 0;
+    S->n = 0;
+    for (int s = 0; s < ZXH_NSYM; s++) S->n += code_len[s] != 0;
+    if (S->n < 4) return 0;
+    const int n = zxh_lengths_cost(code_len, freq, W, base, &S->c0);
 
-    /* symbols by descending (weight, symbol): the order lengths are handed out in */
-    zxh_leaf_t* leaves = W->sort_tmp;
-    int k = 0;
-    for (int s = 0; s < ZXH_NSYM; s++) {
-        if (!freq[s]) continue;
-        leaves[k].w = freq[s];
-        leaves[k].sym = (int16_t)s;
-        k++;
+    /* ranks: symbols by falling (weight, symbol), the order in which a shape hands out its lengths */
+    zxh_leaf_t* up = W->sort_tmp;
+    for (int s = 0, k = 0; s < ZXH_NSYM; s++) {
+        if (freq[s]) {
+            up[k].w = freq[s];
+            up[k++].sym = (int16_t)s;
+        }
     }
-    zxh_sort_leaves(leaves, n);
+    zxh_sort_leaves(up, n);
     W->pf_rank[0] = 0;
     for (int r = 0; r < n; r++) {
-        W->sym_order[r] = leaves[n - 1 - r].sym;
-        W->pf_rank[r + 1] = W->pf_rank[r] + leaves[n - 1 - r].w;
+        W->sym_order[r] = up[n - 1 - r].sym;
+        W->pf_rank[r + 1] = W->pf_rank[r] + up[n - 1 - r].w;
     }
 
-    int n_cand = 0;
-    { /* candidate 1: greedy walk */
-        uint32_t blc_w[ZXH_LU + 1];
-        zxh_walk(blc0, W->pf_rank, n, max_code_len, blc_w);
-        uint8_t* cl = W->cand[n_cand];
-        for (int s = 0; s < ZXH_NSYM; s++) cl[s] = 0;
-        int r = 0;
-        for (int l = 1; l <= ZXH_LU; l++)
-            for (uint32_t q = 0; q < blc_w[l]; q++) cl[W->sym_order[r++]] = (uint8_t)l;
-        n_cand++;
+    /* candidate: the greedy walk */
+    uint32_t shape[ZXH_LU + 1];
+    zxh_walk(base, W->pf_rank, n, max_code_len, shape);
+    zxh_lengths_from_shape(shape, ZXH_LU, 0, n, freq, W->sym_order, W->cand[S->n_cand++]);
+
+    /* candidates: package-merge again with the longest code one and two bits shorter, while the alphabet fits */
+    int longest = ZXH_LU;
+    while (longest > 0 && !base[longest]) longest--;
+    for (int cap2 = longest - 1; cap2 >= longest - 2 && cap2 >= 2 && (1u << cap2) >= (uint32_t)n; cap2--) {
+        if (zxh_build_code_lengths(freq, W->cand[S->n_cand], cap2, W) != 0) break;
+        S->n_cand++;
     }
-    int max_len0 = 0;
-    for (int l = ZXH_LU; l >= 1; l--) {
-        if (blc0[l]) {
-            max_len0 = l;
-            break;
-        }
-    }
-    if (max_len0 >= 2) { /* candidates 2-3: plain package-merge with the cap lowered by 1 and 2 */
-        for (int cut = 1; cut <= 2; cut++) {
-            const int cap2 = max_len0 - cut;
-            if (cap2 < 2 || (1u << cap2) < (uint32_t)n) break;
-            if (zxh_build_code_lengths(freq, W->cand[n_cand], cap2, W) != 0) break;
-            n_cand++;
-        }
-    }
-    S->n_cand = n_cand;
-    /* candidate 4: exact DP over groups of 1, 2 or 4 symbols */
+
+    /* candidate: the exact DP over groups of 1, 2 or 4 ranks (at most ZXH_DP_M of them) */
     S->g_log2 = n <= 64 ? 0 : (n <= 128 ? 1 : 2);
-    const int g = 1 << S->g_log2;
-    S->m = (n + g - 1) / g;
+    S->m = (n + (1 << S->g_log2) - 1) >> S->g_log2;
     S->cap_c = max_code_len - S->g_log2;
     if (S->m >= 2 && S->cap_c >= 1 && S->m <= (1 << S->cap_c)) {
-        for (int j2 = 0; j2 <= S->m; j2++) {
-            int r = j2 * g;
-            if (r > n) r = n;
-            W->pfg[j2] = W->pf_rank[r];
-        }
+        for (int q = 0; q <= S->m; q++) W->pfg[q] = W->pf_rank[(q << S->g_log2) < n ? (q << S->g_log2) : n];
         S->do_dp = 1;
     }
     return 1;
@@ -515,59 +516,29 @@ ZXH int zxh_nudge_begin(const uint32_t* freq, const uint8_t* code_len, int max_c
 /* dp_ok / cblc: result of the grouped DP (ignored unless S->do_dp); 1 if code_len was replaced */
 ZXH int zxh_nudge_end(const uint32_t* freq, uint8_t* code_len, zxh_work_t* W, const zxh_nudge_t* S, int dp_ok,
                       const uint32_t* cblc) {
-    const int n = S->n, g_log2 = S->g_log2, g = 1 << S->g_log2;
     int n_cand = S->n_cand;
-    if (S->do_dp && dp_ok) {
-        uint8_t* cl = W->cand[n_cand];
-        for (int s = 0; s < ZXH_NSYM; s++) cl[s] = 0;
-        int r = 0, ghosts = 0;
-        uint8_t ghost_len = 0;
-        for (int lc = 1; lc <= S->cap_c; lc++) {
-            for (uint32_t q = 0; q < cblc[lc]; q++) {
-                for (int e = 0; e < g; e++, r++) {
-                    if (r < n) cl[W->sym_order[r]] = (uint8_t)(lc + g_log2);
-                    else {
-                        ghost_len = (uint8_t)(lc + g_log2);
-                        ghosts++;
-                    }
-                }
-            }
-        }
-        for (int s = 0; s < ZXH_NSYM && ghosts; s++) { /* pad the last group with absent symbols */
-            if (freq[s] == 0 && cl[s] == 0) {
-                cl[s] = ghost_len;
-                ghosts--;
-            }
-        }
-        n_cand++;
-    }
-    const uint64_t j0 = zxh_j(&S->c0);
-    uint64_t best_j = j0;
-    int best = -1;
-    for (int ci = 0; ci < n_cand; ci++) {
-        int valid = 1;
-        for (int s = 0; s < ZXH_NSYM; s++) {
-            if (freq[s] != 0 && W->cand[ci][s] == 0) {
-                valid = 0;
-                break;
-            }
-        }
-        if (!valid) continue;
-        uint32_t blc[ZXH_LU + 1];
-        (void)zxh_classes(W->cand[ci], blc);
-        zxh_prefix_masses(W->cand[ci], freq, blc, W->pf, W->val);
-        zxh_cost_t c1;
-        zxh_eval(blc, W->pf, &c1);
-        if (c1.bits * 1000 > S->c0.bits * ZXH_BITS_PERMIL) continue;
-        if (c1.touches * 256 > S->c0.touches * ZXH_MERGE_Q8) continue;
-        const uint64_t j = zxh_j(&c1);
-        if (j < best_j) {
-            best_j = j;
-            best = ci;
+    if (S->do_dp && dp_ok)
+        zxh_lengths_from_shape(cblc, S->cap_c, S->g_log2, S->n, freq, W->sym_order, W->cand[n_cand++]);
+    /* adopt the cheapest candidate that covers the alphabet, costs at most 1.5 % more bits and saves at least a
+     * tenth of the decoder's work; the first one wins a tie */
+    uint64_t best = zxh_j(&S->c0);
+    const uint8_t* winner = 0;
+    for (int q = 0; q < n_cand; q++) {
+        const uint8_t* cl = W->cand[q];
+        int holes = 0;
+        for (int s = 0; s < ZXH_NSYM; s++) holes |= (freq[s] != 0) & (cl[s] == 0);
+        if (holes) continue;
+        uint32_t cnt[ZXH_LU + 1];
+        zxh_cost_t c;
+        (void)zxh_lengths_cost(cl, freq, W, cnt, &c);
+        if (c.bits * 1000 > S->c0.bits * ZXH_BITS_PERMIL || c.work * 256 > S->c0.work * ZXH_MERGE_Q8) continue;
+        if (zxh_j(&c) < best) {
+            best = zxh_j(&c);
+            winner = cl;
         }
     }
-    if (best < 0) return 0;
-    for (int s = 0; s < ZXH_NSYM; s++) code_len[s] = W->cand[best][s];
+    if (!winner) return 0;
+    for (int s = 0; s < ZXH_NSYM; s++) code_len[s] = winner[s];
     return 1;
 }
 
