@@ -69,7 +69,9 @@ extern "C" uint64_t simt_decode_blocks(const u8* src, uint64_t src_size, u8* dst
             simt_bar_base = smem_addr(ring) + RING_BYTES + ST_OFF_BAR;
             st_init(smem_addr(ring) + RING_BYTES, lane);
 #endif
-            const int r = units ? decode_job<true>(P, job, scr, ring, lane) : decode_job<false>(P, job, scr, ring, lane);
+            const bool has_dict = P.dict != nullptr && P.dict_size != 0;
+            const int r = units ? (has_dict ? decode_job<true, true>(P, job, scr, ring, lane) : decode_job<true, false>(P, job, scr, ring, lane))
+                                : (has_dict ? decode_job<false, true>(P, job, scr, ring, lane) : decode_job<false, false>(P, job, scr, ring, lane));
             flush_wait(lane);
             __syncwarp();
             if (lane == 0) status[j] = r;

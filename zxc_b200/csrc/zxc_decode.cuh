@@ -4,15 +4,18 @@
  * One warp per independent block; lane = sequence,
  * 32 sequences per batch:
  *   1. token / offset unpack               (GLO zxc_decompress.c:626-694, GHI :701-727)
- *   2. escape resolution over the extras   (varint, :51-88): the batch's k escapes are walked
- *      once, warp-uniformly; each lane keeps the value(s) whose ordinal (ballot + popc) is its own
+ *   2. escape resolution over the extras   (varint, :51-88): every value of the section is computed once per block
+ *      by a segment-map scan; a lane takes the value(s) whose ordinal (ballot + popc) is its own
  *   3. warp prefix sums -> literal source offset and output offset per lane
  *   4. bounds / offset validation; first failing lane == first failing sequence
- *   5. literal copies (independent), then match copies in dependency rounds: a match is ready
- *      when its source ends below the lowest pending match destination
+ *   5. two copy passes -- every literal run, then every match whose source ends at or below the batch's first output
+ *      byte (short items per lane, long ones as balanced 16-byte chunks over the warp) -- and the matches that read
+ *      the batch's own output one after the other in sequence order
  *   6. the output is staged in a per-warp shared-memory ring and leaves the SM as coalesced
  *      16-byte stores (512 B per warp instruction); match sources come from the ring when they
  *      are recent and from global memory (L2) once flushed.
+ * The block format and the presence of a dictionary are template parameters (decode_lz_block<UNITS, GHI, HAS_DICT>).
+ * zxc_decode_stage.cuh holds the opt-in TMA flavour (sections staged by cp.async.bulk, ring flushed by bulk stores).
  * Overlapping matches (off < ml) use the period-`off` index instead of the reference's shuffle
  * tables (:197-413).  Output is written exactly (no wild-copy overshoot): none of the
  * reference's PAD / TAIL_PAD slack is needed on the destination; the wire-level 32-byte
@@ -464,39 +467,6 @@ __device__ __forceinline__ void flush_wait(u32 lane) {
 #endif
 }
 
-/* whole-warp copy of n bytes from a generic source pointer into the ring at dpos, 128 bytes per
- * iteration: lane = destination word, two aligned source words funnel-shifted onto it.  Caller
- * guarantees no ring wrap on the destination, sp - 7 readable, and that every 128-byte step only
- * reads bytes that were complete before the step started (no self-overlap closer than 132). */
-__device__ __forceinline__ void warp_copy_words_to_ring(u8* ring, u32 dpos, const u8* sp, u32 n, u32 lane) {
-    const u32 da = dpos & 3u;
-    u8* dbyte = ring + (dpos & (RING_BYTES - 1));
-    const u32 ff = da ? 1u : 0u;
-    const u32 lfe = (da + n) >> 2;
-    const u32 tb = (da + n) & 3u;
-    /* edge bytes: lanes 0..2 the head, lanes 4..6 the tail */
-    if (da && lane < min(4u - da, n)) dbyte[lane] = sp[lane];
-    const u8* bp = sp - da;
-    const u32 m = (u32)(reinterpret_cast<uintptr_t>(bp)) & 3u;
-    const u32* wp = reinterpret_cast<const u32*>(bp - m);
-    u32* dw = reinterpret_cast<u32*>(dbyte - da);
-    const u32 sh = m * 8u;
-    for (u32 j0 = 0; j0 < lfe; j0 += 32) {
-        const u32 j = j0 + lane;
-        if (j >= ff && j < lfe) {
-            const u32 a = wp[j];
-            const u32 b = m ? wp[j + 1] : 0u;
-            dw[j] = __funnelshift_r(a, b, sh);
-        }
-        __syncwarp();
-    }
-    /* tail bytes last: with a self-overlapping source they are produced by the loop above */
-    if (tb && (lfe > 0 || da == 0) && lane < tb) {
-        const u32 t0 = n - tb + lane;
-        dbyte[t0] = sp[t0];
-    }
-}
-
 /* whole-warp match copy of n bytes into the ring at d from distance off */
 __device__ __forceinline__ void warp_match_to_ring(const Window& w, u32 d, u32 off, u32 n, u32 lane) {
     const u32 mask = RING_BYTES - 1;
@@ -536,59 +506,13 @@ __device__ __forceinline__ void warp_match_global(const Window& w, u32 d, u32 of
 }
 
 /* ------------------------------------------------------------------------- */
-/* per-lane copy of n bytes (n <= 4*NWORDS - 4) into the ring, word granular:   */
-/* aligned 4-byte source words are funnel-shifted onto the destination's word   */
-/* grid; whole destination words go out as STS.32, the <= 3 + 3 edge bytes as   */
-/* byte stores (neighbouring lanes own the other bytes of those words).         */
-/* `sp` is a generic pointer (ring or global).  Caller guarantees: no ring wrap */
-/* on either side, and that sp - 7 is readable.                                 */
-/* ------------------------------------------------------------------------- */
-template <int NWORDS>
-__device__ __forceinline__ void lane_copy_words(u8* ring, u32 dpos, const u8* sp, u32 n, bool on) {
-    const u32 da = dpos & 3u;
-    u8* dbyte = ring + (dpos & (RING_BYTES - 1));
-    if (on) {
-        const u32 ff = da ? 1u : 0u;        /* first whole destination word */
-        const u32 lfe = (da + n) >> 2;      /* one past the last whole destination word */
-        const u32 tb = (da + n) & 3u;       /* bytes in the trailing partial word */
-        /* head bytes [da, min(4, da+n)) of destination word 0 */
-        if (da) {
-            const u32 hn = min(4u - da, n);
-            if (hn > 0) dbyte[0] = sp[0];
-            if (hn > 1) dbyte[1] = sp[1];
-            if (hn > 2) dbyte[2] = sp[2];
-        }
-        /* tail bytes of destination word lfe (unless the head already covered a lone word 0) */
-        if (tb && (lfe > 0 || da == 0)) {
-            const u32 t0 = n - tb;
-            dbyte[t0] = sp[t0];
-            if (tb > 1) dbyte[t0 + 1] = sp[t0 + 1];
-            if (tb > 2) dbyte[t0 + 2] = sp[t0 + 2];
-        }
-        if (lfe > ff) {
-            const u8* bp = sp - da;
-            const u32 m = (u32)(reinterpret_cast<uintptr_t>(bp)) & 3u;
-            const u32* wp = reinterpret_cast<const u32*>(bp - m);
-            u32* dw = reinterpret_cast<u32*>(dbyte - da);
-            const u32 sh = m * 8u;
-            const u32 nw = lfe + (m ? 1u : 0u);
-            u32 W[NWORDS + 1];
-#pragma unroll
-            for (int k = 0; k <= NWORDS; k++) W[k] = ((u32)k >= ff && (u32)k < nw) ? wp[k] : 0u;
-#pragma unroll
-            for (int k = 0; k < NWORDS; k++)
-                if ((u32)k >= ff && (u32)k < lfe) dw[k] = __funnelshift_r(W[k], W[k + 1], sh);
-        }
-    }
-}
-
-/* ------------------------------------------------------------------------- */
-/* the same copy without byte loads and without branches (ZXC_LANECOPY2): the   */
+/* per-lane copy of n bytes (n <= 4*NWORDS - 4) into the ring, branch-free: the  */
 /* NWORDS + 1 aligned source words that cover the item are loaded once, shifted  */
 /* onto the destination grid in registers, and the partial words at either end   */
 /* leave as byte / halfword stores of those registers (a neighbouring lane owns  */
-/* the other bytes of such a word, so no read-modify-write).  Same contract as    */
-/* lane_copy_words; reads up to 3 bytes before sp and 7 past sp + n.              */
+/* the other bytes of such a word, so no read-modify-write).  `sp` is a generic   */
+/* pointer (ring or global); the caller guarantees no ring wrap on either side;   */
+/* reads up to 6 bytes before sp and 7 past sp + n.                               */
 /* ------------------------------------------------------------------------- */
 /* whole words K .. N-1 of a per-lane copy: word k is stored when k < kt (constant offsets, unrolled at compile time) */
 template <int K, int N>
@@ -646,66 +570,13 @@ __device__ __forceinline__ void lane_copy_words2(u32 ring_s, u32 dpos, const u8*
 }
 
 /* ------------------------------------------------------------------------- */
-/* long items, four at a time: each 8-lane group copies one item into the ring,  */
-/* 32 bytes per step (lane = destination word).  Items of one call are mutually  */
-/* independent; an item may overlap itself only at distance >= 36.  Owners hold   */
-/* (dpos, generic source pointer, n) for their item; m_items has one bit per owner.*/
-/* ------------------------------------------------------------------------- */
-__device__ __forceinline__ void group4_copy_words(u8* ring, u32 m_items, u32 my_d, const u8* my_sp, u32 my_n,
-                                                  u32 lane) {
-    const u32 g = lane >> 3, sub = lane & 7u;
-    const unsigned long long my_sp64 = reinterpret_cast<unsigned long long>(my_sp);
-    while (m_items) {
-        int jsel = -1;
-#pragma unroll
-        for (u32 q = 0; q < 4; q++) {
-            const int j = m_items ? __ffs(m_items) - 1 : -1;
-            if (m_items) m_items &= m_items - 1;
-            if (q == g) jsel = j;
-        }
-        const bool on = jsel >= 0;
-        const int jj = on ? jsel : 0;
-        const u32 dpos = __shfl_sync(FULL, my_d, jj);
-        const u32 n_item = __shfl_sync(FULL, my_n, jj);
-        const u32 n = on ? n_item : 0u;
-        const u8* sp = reinterpret_cast<const u8*>(__shfl_sync(FULL, my_sp64, jj));
-        const u32 da = dpos & 3u;
-        u8* dbyte = ring + (dpos & (RING_BYTES - 1));
-        const u32 ff = da ? 1u : 0u;
-        const u32 lfe = (da + n) >> 2;
-        const u32 tb = (da + n) & 3u;
-        if (on && da && sub < min(4u - da, n)) dbyte[sub] = sp[sub];
-        const u8* bp = sp - da;
-        const u32 m = (u32)(reinterpret_cast<uintptr_t>(bp)) & 3u;
-        const u32* wp = reinterpret_cast<const u32*>(bp - m);
-        u32* dw = reinterpret_cast<u32*>(dbyte - da);
-        const u32 sh = m * 8u;
-        const u32 iters = __reduce_max_sync(FULL, (lfe + 7u) >> 3);
-        for (u32 it = 0; it < iters; it++) {
-            const u32 j = it * 8u + sub;
-            if (on && j >= ff && j < lfe) {
-                const u32 a = wp[j];
-                const u32 b = m ? wp[j + 1] : 0u;
-                dw[j] = __funnelshift_r(a, b, sh);
-            }
-            __syncwarp();
-        }
-        if (on && tb && (lfe > 0 || da == 0) && sub < tb) {
-            const u32 t0 = n - tb + sub;
-            dbyte[t0] = sp[t0];
-        }
-        __syncwarp();
-    }
-}
-
-/* ------------------------------------------------------------------------- */
-/* long items of one pass, all at once (ZXC_BALANCED): every aligned run of four  */
+/* long items of one pass, all at once: every aligned run of four                 */
 /* whole destination words of every item is one lane's work, so a pass moves up   */
 /* to 512 bytes per step and -- what matters -- pays ONE memory round trip per    */
-/* step: group4_copy_words above moves 32 bytes of an item per round trip (its    */
-/* loop must order each step's loads behind the previous step's stores), and two  */
-/* thirds of the corpus' bytes sit in items longer than 64 bytes that come from   */
-/* global memory.  Items of one call are mutually independent and do not overlap  */
+/* step (round 1 moved 32 bytes of an item per round trip, four items at a time: */
+/* its loop had to order each step's loads behind the previous step's stores),    */
+/* and two thirds of the corpus' bytes sit in items longer than 64 bytes that     */
+/* come from global memory.  Items of one call are mutually independent and do not overlap  */
 /* themselves (distance >= length), so no chunk reads what another one writes;    */
 /* the aligned words a chunk loads may reach 3 bytes into a neighbour's           */
 /* destination, those bytes are shifted out.  Owners hold (dpos, source, n).      */
@@ -775,56 +646,6 @@ __device__ __forceinline__ void balanced_copy_words(u32 ring_s, u32 m_items, u32
     }
 }
 
-#ifndef ZXC_BALANCED
-#define ZXC_BALANCED 1
-#endif
-#ifndef ZXC_LANECOPY2
-#define ZXC_LANECOPY2 1
-#endif
-#ifndef ZXC_OPAQUE_LANE
-#define ZXC_OPAQUE_LANE 0
-#endif
-#ifndef ZXC_PF_STREAM
-#define ZXC_PF_STREAM 0
-#endif
-#ifndef ZXC_PF_FAR
-#define ZXC_PF_FAR 0
-#endif
-#if defined(__CUDACC__)
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-#else
-static inline void prefetch_l2(const void*) {}
-static inline void prefetch_l1(const void*) {}
-#endif
-#ifndef ZXC_COLD_CALLS
-#define ZXC_COLD_CALLS 0
-#endif
-#if ZXC_COLD_CALLS
-/* the byte paths of the pass loop as one out-of-line call: they serve a few items per block, and inlined they sit in
- * the middle of the loop the instruction cache has to hold */
-__device__ __noinline__ void slow_item(u8* ring, u8* out, const u8* dict, u32 dict_size, i32 near_lo, const u8* lit,
-                                       u32 d, u32 n, u32 aux, u32 lane) {
-    if (lit) {
-#pragma unroll 1
-        for (u32 k = lane; k < n; k += 32) ring[(d + k) & (RING_BYTES - 1)] = lit[aux + k];
-    } else {
-        Window w;
-        w.ring = ring;
-        w.out = out;
-        w.dict = dict;
-        w.dict_size = dict_size;
-        w.near_lo = near_lo;
-        warp_match_to_ring(w, d, aux, n, lane);
-    }
-}
-#endif
-#ifndef ZXC_FUSE2
-#define ZXC_FUSE2 0 /* needs ZXC_SERIAL_TAIL and ZXC_LANECOPY2 */
-#endif
-#ifndef ZXC_SERIAL_TAIL
-#define ZXC_SERIAL_TAIL 1
-#endif
 #ifndef ZXC_NW
 #define ZXC_NW 8 /* destination words a per-lane copy may touch: items up to 4 * ZXC_NW - 4 bytes are "short" (6: -3.6 %, 10: +0.1 %) */
 #endif
@@ -834,10 +655,16 @@ __device__ __noinline__ void slow_item(u8* ring, u8* out, const u8* dict, u32 di
 /* ------------------------------------------------------------------------- */
 /* GLO / GHI block body.  Returns decoded bytes or a negative zxc_error_t.    */
 /* ------------------------------------------------------------------------- */
-template <bool UNITS>
-__device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 cap, const u8* dict,
-                               u32 dict_size, const u8* dict_huf, u8* scratch, u32 scratch_cap, u8* ring,
+/* GHI and HAS_DICT are compile-time: the loop below sits at the kernel's register limit, and every branch and live
+ * value it does not carry (the other block format's unpack, the dictionary pointer and its source classification)
+ * is code the instruction cache does not hold and a register that is not spilled. */
+template <bool UNITS, bool GHI, bool HAS_DICT>
+__device__ int decode_lz_block(const u8* pay, u32 comp, u8* out, u32 cap, const u8* dict_in,
+                               u32 dict_size_in, const u8* dict_huf, u8* scratch, u32 scratch_cap, u8* ring,
                                u32 lane, u32 P_flags) {
+    constexpr bool ghi = GHI;
+    const u8* dict = HAS_DICT ? dict_in : (const u8*)0;
+    const u32 dict_size = HAS_DICT ? dict_size_in : 0u;
     Sections S;
     const int prc = parse_sections(pay, comp, ghi, cap, dict_huf, scratch, scratch_cap, lane, S);
     if (prc != ZXC_OK) return prc;
@@ -904,31 +731,22 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
     }
 
 #if ZXC_STAGE
-    /* the token / offset sections come through shared memory (zxc_decode_stage.cuh); Huffman-decoded tokens sit in the
-     * scratch and are read from there */
-    const u32 tok_w = ghi ? 4u : 1u, off_w = enc_off ? 1u : 2u;
-    const u32 tx0 = (u32)(reinterpret_cast<uintptr_t>(tok) & 15u), ox0 = (u32)(reinterpret_cast<uintptr_t>(offs) & 15u);
+    /* the token / offset sections (and raw literals) come through shared memory (zxc_decode_stage.cuh); Huffman-decoded
+     * tokens and expanded literals sit in the scratch and are read from there */
     const u32 stage_s = smem_addr(ring) + RING_BYTES;
-    {
-        SeqStream t = st_tok(stage_s), o = st_off(stage_s);
-        const u32 ct = t.open(tok, tok_w * n_seq, pay + comp, tok >= pay && tok < pay + comp, tx0 + tok_w * min(32u, n_seq), lane);
-        const u32 co = o.open(offs, ghi ? 0u : off_w * n_seq, pay + comp, !ghi, ox0 + off_w * min(32u, n_seq), lane);
-        sts32<0>(stage_s + ST_OFF_STATE, ct); /* every lane writes the same words and later reads what it wrote */
-        sts32<4>(stage_s + ST_OFF_STATE, co);
+    TokStream::open(stage_s, tok, (ghi ? 4u : 1u) * n_seq, pay + comp, tok >= pay && tok < pay + comp);
+    OffStream::open(stage_s, ghi ? tok : offs, ghi ? 0u : (enc_off ? 1u : 2u) * n_seq, pay + comp, !ghi);
 #if ZXC_STAGE_LIT
-        lit_open(stage_s, lit, n_lit_avail, pay + comp, lit >= pay && lit < pay + comp); /* raw literals only */
-#endif
-    }
-#if ZXC_STAGE_LIT
-#define ST_LIT_CLOSE() lit_close(stage_s)
+    LitStream::open(stage_s, lit, n_lit_avail, pay + comp, lit >= pay && lit < pay + comp);
+#define ST_LIT_CLOSE() LitStream::close(stage_s)
 #else
 #define ST_LIT_CLOSE() do { } while (0)
 #endif
-#define ST_CLOSE()                                                                                   \
-    do {                                                                                             \
-        st_tok(stage_s).close(tx0 + tok_w * base, tx0 + tok_w * min(base + 32u, n_seq));             \
-        st_off(stage_s).close(ox0 + off_w * base, ox0 + off_w * min(base + 32u, n_seq));             \
-        ST_LIT_CLOSE();                                                                              \
+#define ST_CLOSE()                   \
+    do {                             \
+        TokStream::close(stage_s);   \
+        OffStream::close(stage_s);   \
+        ST_LIT_CLOSE();              \
     } while (0)
 #else
 #define ST_CLOSE() do { } while (0)
@@ -942,9 +760,12 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
         const bool valid = i < n_seq;
         u32 ll = 0, ml = 0, off = 1;
 #if ZXC_STAGE
+        const u32 tok_w = ghi ? 4u : 1u, off_w = enc_off ? 1u : 2u;
+        const u32 tx0 = (u32)(reinterpret_cast<uintptr_t>(tok) & 15u), ox0 = (u32)(reinterpret_cast<uintptr_t>(offs) & 15u);
         const u32 i_end = min(base + 32u, n_seq);
-        const SeqStream st_t = st_tok(stage_s), st_o = st_off(stage_s);
-        const bool t_st = st_t.staged(tx0 + tok_w * i_end), o_st = st_o.staged(ox0 + off_w * i_end);
+        const StWindow st_t = TokStream::need(stage_s, tok, tx0 + tok_w * base, tx0 + tok_w * i_end, 0u, lane);
+        const StWindow st_o = OffStream::need(stage_s, offs, ox0 + off_w * base, ox0 + off_w * i_end, 0u, lane);
+        const bool t_st = tx0 + tok_w * i_end <= st_t.hi, o_st = !ghi && ox0 + off_w * i_end <= st_o.hi;
 #endif
         if (valid) {
             u32 a, b = 0;
@@ -1057,12 +878,6 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
             ord_base += q;
             if (!use_vals)
                 for (u32 s = 0; s < q; s++) epos = varint_advance(ext, epos, ext_end); /* rare: re-walk */
-#if ZXC_STAGE
-            st_t.step(tok, tx0 + tok_w * base, tx0 + tok_w * i_end, tx0 + tok_w * (base + 1u),
-                        tx0 + tok_w * min(base + 33u, n_seq), lane);
-            st_o.step(offs, ox0 + off_w * base, ox0 + off_w * i_end, ox0 + off_w * (base + 1u),
-                        ox0 + off_w * min(base + 33u, n_seq), lane);
-#endif
             base += 1;
             continue;
         }
@@ -1080,16 +895,7 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
         const u32 T = __shfl_sync(FULL, s_tot, m - 1), TL = __shfl_sync(FULL, s_ll, m - 1);
 #if ZXC_STAGE && ZXC_STAGE_LIT
         const u32 lx0 = (u32)(reinterpret_cast<uintptr_t>(lit) & 15u);
-        const LitWindow lw = lit_need(stage_s, lit, lx0 + L, lx0 + L + TL, lane);
-#endif
-#if ZXC_PF_STREAM
-        /* the three input streams advance linearly: ask for the sectors the next batches will read while this one copies */
-        if (lane < 4) {
-            const u8* p = lane == 0 ? tok + (size_t)(ghi ? 4u : 1u) * (base + ZXC_PF_STREAM * 32u)
-                        : lane == 1 ? (offs ? offs + (size_t)(enc_off ? 1u : 2u) * (base + ZXC_PF_STREAM * 32u) : tok)
-                                    : lit + L + TL + 128u * (lane - 2u) + 64u * ZXC_PF_STREAM;
-            prefetch_l2(p);
-        }
+        const StWindow lw = LitStream::need(stage_s, lit, lx0 + L, lx0 + L + TL, 8u, lane);
 #endif
         {
             const i32 a = (i32)(O + T) - (i32)RING_BYTES + 32;
@@ -1114,40 +920,10 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
                                (near ? (si >= 8 && si + ml + 8 <= RING_BYTES)
                                      : (in_dict || (src_lo >= 8 && src_lo + (i32)ml + 4 <= w.near_lo)));
         const bool m_lane_ok = m_word_ok && ml <= MATCH_SHORT && off >= ml;
-#if ZXC_BALANCED
         const bool m_grp_ok = m_word_ok && !m_lane_ok && off >= ml; /* chunks of one item run side by side */
-#else
-        const bool m_grp_ok = m_word_ok && !m_lane_ok && off >= 36;
-#endif
         const u8* m_sp = near ? ring + si : (src_lo < 0 ? dict + ((i32)dict_size + src_lo) : out + src_lo);
-#if ZXC_PF_FAR
-        if (act && !near && src_lo >= 0) prefetch_l1(m_sp); /* far sources start travelling while the literals are copied */
-#endif
         const bool l_word_ok = (out_start & mask) + ll + 4 <= RING_BYTES;
 
-#if !ZXC_SERIAL_TAIL
-        /* ---- dependency masks ---- */
-        /* exact dependencies: a match waits only for the earlier matches of this batch whose
-         * destination [mdst_i, mend_i) intersects its source [src_lo, src_end).  Destinations are
-         * ordered by lane, so the blockers are a lane interval [a, b) found by two binary searches
-         * over the warp (shuffle as the array read). */
-        u32 depmask;
-        {
-            const u32 mend = mdst + ml;
-            u32 lo_a = 0, hi_a = lane, lo_b = 0, hi_b = lane; /* blockers are strictly earlier lanes */
-#pragma unroll
-            for (int it = 0; it < 5; it++) {
-                const u32 mid_a = (lo_a + hi_a) >> 1, mid_b = (lo_b + hi_b) >> 1;
-                const i32 e_a = (i32)__shfl_sync(FULL, mend, mid_a);
-                const i32 d_b = (i32)__shfl_sync(FULL, mdst, mid_b);
-                if (lo_a < hi_a) { if (e_a > src_lo) hi_a = mid_a; else lo_a = mid_a + 1; }   /* first lane with mend > src_lo */
-                if (lo_b < hi_b) { if (d_b < src_end) lo_b = mid_b + 1; else hi_b = mid_b; }   /* first lane with mdst >= src_end */
-            }
-            const u32 below_b = lo_b >= 32 ? 0xFFFFFFFFu : ((1u << lo_b) - 1u);
-            const u32 below_a = lo_a >= 32 ? 0xFFFFFFFFu : ((1u << lo_a) - 1u);
-            depmask = below_b & ~below_a;
-        }
-#else
         /* ---- dependencies ---- */
         /* A match whose source ends at or below O -- the first output byte of this batch -- reads nothing the batch
          * writes: such matches (94 % of them on the bench corpus) go side by side in one pass after the literals.  The
@@ -1155,36 +931,9 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
          * sequential order is the reference's order, so no dependency analysis is needed, and a chain of 32 dependent
          * matches costs 32 short steps instead of 32 passes. */
         const bool m_free = src_end <= (i32)O;
-#endif
         /* ---- pass loop ---- */
-#if !ZXC_SERIAL_TAIL
-        u32 pending = __ballot_sync(FULL, act);
-#endif
         ZXC_STAT(0, 1);            /* batches */
         ZXC_STAT(1, m);            /* sequences */
-#if defined(ZXC_STAT_SIM) && !ZXC_SERIAL_TAIL
-        { /* emulator only: passes the batch would take if pass 0 also served the matches whose source ends below O */
-            const bool fr = act && m_lane_ok && src_end <= (i32)O;
-            const u32 m_fr = __ballot_sync(FULL, fr);
-            const u32 nl = __popc(__ballot_sync(FULL, act && ll > 0 && l_word_ok && ll <= LIT_SHORT));
-            const bool served = fr && (u32)__popc(m_fr & lt_mask) + nl < 32u;
-            u32 pn = pending & ~__ballot_sync(FULL, served);
-            u32 lv = 1;
-            while (pn) {
-                const bool rd = ((pn >> lane) & 1u) && (pn & depmask) == 0;
-                pn &= ~__ballot_sync(FULL, rd);
-                lv++;
-            }
-            ZXC_STAT(9, lv);
-            ZXC_STAT(10, __popc(m_fr));
-            ZXC_STAT(11, __popc(__ballot_sync(FULL, served)));
-        }
-#endif
-#if ZXC_FUSE2
-        /* the two per-lane copies back to back: neither reads what the other writes, so their loads travel together */
-        lane_copy_words2<ZXC_NW>(ring_s, out_start, lit + lit_start, ll, act && ll > 0 && l_word_ok && ll <= LIT_SHORT);
-        lane_copy_words2<ZXC_NW>(ring_s, mdst, m_sp, ml, act && m_free && m_lane_ok);
-#endif
         bool lit_pass = true;
 #pragma unroll 1
         for (;;) {
@@ -1207,23 +956,14 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
                 lok = l_word_ok && ll <= LIT_SHORT;
                 gok = l_word_ok && ll > LIT_SHORT;
             } else {
-#if ZXC_SERIAL_TAIL
                 ready = act && m_free;
-#else
-                ready = ((pending >> lane) & 1u) && (pending & depmask) == 0;
-#endif
                 it_d = mdst;
                 it_n = ml;
                 it_sp = m_sp;
                 lok = m_lane_ok;
                 gok = m_grp_ok;
             }
-#if ZXC_FUSE2
-#elif ZXC_LANECOPY2
             lane_copy_words2<ZXC_NW>(ring_s, it_d, it_sp, it_n, ready && lok);
-#else
-            lane_copy_words<ZXC_NW>(ring, it_d, it_sp, it_n, ready && lok);
-#endif
             const u32 m_grp = __ballot_sync(FULL, ready && gok);
             ZXC_STAT(2, 1);                                           /* passes */
             ZXC_STAT(3, __popc(__ballot_sync(FULL, ready && lok)));   /* per-lane items */
@@ -1231,29 +971,20 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
             ZXC_STAT(5, m_grp != 0);                                  /* long-copy calls */
             ZXC_STAT(6, __popc(__ballot_sync(FULL, ready && !lok && !gok))); /* slow items */
             ZXC_STAT(7, __ballot_sync(FULL, ready && lok) != 0);      /* passes with a per-lane item */
-#if ZXC_BALANCED
             if (m_grp) balanced_copy_words(ring_s, m_grp, it_d, it_sp, it_n, lane);
-#else
-            if (m_grp) group4_copy_words(ring, m_grp, it_d, it_sp, it_n, lane);
-#endif
             u32 m_slow = __ballot_sync(FULL, ready && !lok && !gok);
             while (m_slow) { /* ring wrap, close overlap, dictionary, straddling sources: byte paths */
                 const int j = __ffs(m_slow) - 1;
                 m_slow &= m_slow - 1;
                 const u32 d = __shfl_sync(FULL, it_d, j), n = __shfl_sync(FULL, it_n, j);
                 const u32 aux = __shfl_sync(FULL, lit_pass ? lit_start : off, j);
-#if ZXC_COLD_CALLS
-                slow_item(ring, out, dict, dict_size, w.near_lo, lit_pass ? lit : (const u8*)0, d, n, aux, lane);
-#else
                 if (lit_pass) {
                     for (u32 k = lane; k < n; k += 32) ring[(d + k) & mask] = lit[aux + k];
                 } else {
                     warp_match_to_ring(w, d, aux, n, lane);
                 }
-#endif
             }
             __syncwarp();
-#if ZXC_SERIAL_TAIL
             if (!lit_pass) break;
             lit_pass = false;
         }
@@ -1275,12 +1006,6 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
                 __syncwarp();
             }
         }
-#else
-            if (lit_pass) lit_pass = false;
-            else pending &= ~__ballot_sync(FULL, ready);
-            if (!pending) break;
-        }
-#endif
 
         /* ---- advance and flush ---- */
         O += T;
@@ -1288,13 +1013,6 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
         ring_flush(w, F, O & ~511u, lane, al16);
         __syncwarp();
 
-#if ZXC_STAGE
-        {   /* the next batch's tokens and offsets: issue what the rings have room for, wait for what it reads */
-            const u32 nb = base + (m < nvalid ? m : 32u), ne = min(nb + 32u, n_seq);
-            st_t.step(tok, tx0 + tok_w * base, tx0 + tok_w * i_end, tx0 + tok_w * nb, tx0 + tok_w * ne, lane);
-            st_o.step(offs, ox0 + off_w * base, ox0 + off_w * i_end, ox0 + off_w * nb, ox0 + off_w * ne, lane);
-        }
-#endif
         if (m < nvalid) {
             const u32 below = (1u << m) - 1u;
             const u32 q = __popc(m_ll & below) + __popc(m_ml & below);
@@ -1321,7 +1039,7 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, bool ghi, u8* out, u32 c
 }
 
 /* zxc_decompress_chunk_wrapper_body (zxc_decompress.c:1646-1695) for one job */
-template <bool UNITS>
+template <bool UNITS, bool HAS_DICT>
 __device__ int decode_job(const DecodeParams& P, const zxc_b200_job_t& job, u8* scratch, u8* ring, u32 lane) {
     const u8* blk = P.src + job.src_off;
     u8* out = P.dst + job.dst_off;
@@ -1336,9 +1054,11 @@ __device__ int decode_job(const DecodeParams& P, const zxc_b200_job_t& job, u8* 
     }
     switch (type) {
         case BT_GLO:
+            return decode_lz_block<UNITS, false, HAS_DICT>(data, comp, out, job.dst_cap, P.dict, P.dict_size, P.dict_huf,
+                                                           scratch, P.block_cap, ring, lane, P.flags);
         case BT_GHI:
-            return decode_lz_block<UNITS>(data, comp, type == BT_GHI, out, job.dst_cap, P.dict, P.dict_size,
-                                   P.dict_huf, scratch, P.block_cap, ring, lane, P.flags);
+            return decode_lz_block<UNITS, true, HAS_DICT>(data, comp, out, job.dst_cap, P.dict, P.dict_size, P.dict_huf,
+                                                          scratch, P.block_cap, ring, lane, P.flags);
         case BT_RAW:
             if (comp > job.dst_cap) return ZXC_ERROR_DST_TOO_SMALL;
             warp_copy(out, data, comp, lane);
@@ -1350,14 +1070,10 @@ __device__ int decode_job(const DecodeParams& P, const zxc_b200_job_t& job, u8* 
     }
 }
 
-template <bool UNITS, bool DEFERRED>
+template <bool UNITS, bool DEFERRED, bool HAS_DICT>
 __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) zxc_decode_kernel(const DecodeParams P) {
     extern __shared__ __align__(16) u8 smem[];
-    u32 lane_id = threadIdx.x & 31;
-#if ZXC_OPAQUE_LANE && defined(__CUDACC__)
-    asm volatile("" : "+r"(lane_id)); /* keep the lane number in a register: ptxas otherwise re-reads SR_TID.X at its uses */
-#endif
-    const u32 lane = lane_id;
+    const u32 lane = threadIdx.x & 31;
     const u32 wic = threadIdx.x >> 5;
     const u32 gwarp = blockIdx.x * WARPS_PER_CTA + wic;
     u8* scratch = P.scratch + (size_t)gwarp * P.scratch_stride + 256; /* lead-in: word loads may start below */
@@ -1375,7 +1091,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) zxc_decode_kernel(co
                 if (k >= n_def) break;
                 const u32 j = P.defer_list[k];
                 const zxc_b200_job_t job = P.jobs[j];
-                const int r = decode_job<UNITS>(P, job, scratch, ring, lane);
+                const int r = decode_job<UNITS, HAS_DICT>(P, job, scratch, ring, lane);
                 flush_wait(lane); /* nothing of this block is still on its way out of the ring */
                 __syncwarp();
                 if (lane == 0) P.status[j] = r;
@@ -1394,7 +1110,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) zxc_decode_kernel(co
                 const unsigned long long j = b + (u32)(__ffs(m) - 1);
                 m &= m - 1;
                 const zxc_b200_job_t job = P.jobs[j];
-                const int r = decode_job<UNITS>(P, job, scratch, ring, lane);
+                const int r = decode_job<UNITS, HAS_DICT>(P, job, scratch, ring, lane);
                 flush_wait(lane); /* nothing of this block is still on its way out of the ring */
                 __syncwarp();
                 if (lane == 0) P.status[j] = r;
@@ -1408,7 +1124,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) zxc_decode_kernel(co
         j = __shfl_sync(FULL, j, 0);
         if (j >= P.n_jobs) break;
         const zxc_b200_job_t job = P.jobs[j];
-        const int r = decode_job<UNITS>(P, job, scratch, ring, lane);
+        const int r = decode_job<UNITS, HAS_DICT>(P, job, scratch, ring, lane);
                 flush_wait(lane); /* nothing of this block is still on its way out of the ring */
         __syncwarp();
         if (lane == 0) P.status[j] = r;

@@ -12,11 +12,11 @@
  * the block is read); a batch that reaches past it takes the plain global loads, as does a stream that does not live
  * in the payload (Huffman-decoded tokens, RLE / Huffman literals sit in the warp's scratch).
  *
- * No counters are kept: with the cursor at x_lo the chunks below issued(x_lo) = min(n_chunks, x_lo / CH + SLOTS) have
- * been issued, and a batch that reads up to x_hi has waited for the chunks below waited(x_hi) = min(n_chunks,
- * ceil(x_hi / CH)); the step from one batch to the next issues / waits for the difference.  The mbarriers are
- * re-initialised per block, so the parity of chunk c is (c / SLOTS) & 1.  A block that ends early waits for the
- * copies between those two marks (close()); a block that runs to its end has waited for all of them.
+ * Nothing of this lives in registers across a batch -- the decode loop is register-bound, every value kept would
+ * be a spill.  A stream's state is two words of the warp's staging area (which sits right behind its output ring,
+ * so its address follows from the ring's): x_clip, and one packed word with the chunks issued (12 bits), the chunks
+ * waited for (12 bits) and the parity the next wait on each slot asks for.  need() brings a stream up to date at
+ * one point per batch; close() waits for what is still in flight when a block ends, early or not.
  *
  * Slot reuse needs no extra fence: the previous batch's shared loads have delivered their values and the warp has
  * passed a __syncwarp() before lane 0 overwrites the slot.
@@ -42,7 +42,7 @@
 #define ST_LIT_CH 512u
 #define ST_LIT_RING (ST_LIT_SLOTS * ST_LIT_CH)
 #define ST_BAR_BYTES 64u                 /* 2 + 2 + 4 mbarriers */
-#define ST_STATE_BYTES 16u               /* x_clip per stream, the literal stream's counters */
+#define ST_STATE_BYTES 32u               /* per stream: x_clip, packed counters */
 #if ZXC_STAGE
 #define STAGE_BYTES (2u * ST_RING + (ZXC_STAGE_LIT ? ST_LIT_RING : 0u) + ST_BAR_BYTES + ST_STATE_BYTES)
 #else
@@ -156,95 +156,89 @@ static inline u32 lds32(u32 a) { u32 v; memcpy(&v, smem + a, 4); return v; }
 static inline const u8* st_generic(u32 a) { return smem + a; }
 #endif
 
-/* One stream.  Nothing of it lives in registers across a batch: the shared addresses follow from the warp's ring
- * address (a warp's staging area sits right behind its output ring), x_clip is a word of that area, and the counters
- * are functions of the cursor (above).  The decode loop is register-bound; every value kept here would be a spill. */
-template <u32 SLOTS, u32 CH>
-struct StageStream {
-    u32 ring_s; /* shared address of the ring (SLOTS * CH bytes); its SLOTS mbarriers sit at bar_s */
-    u32 bar_s;
-    u32 x_clip; /* coordinates below this are staged (a multiple of 16); 0 = stream not staged in this block */
+struct StWindow { u32 ring_s, lo, hi; }; /* coordinates [lo, hi) are in the ring at ring_s + (x % its size) */
 
-    __device__ __forceinline__ u32 n_chunks() const { return (x_clip + CH - 1u) / CH; }
-    __device__ __forceinline__ u32 issued_at(u32 x_lo) const { return min(n_chunks(), x_lo / CH + SLOTS); }
-    __device__ __forceinline__ u32 waited_at(u32 x_hi) const { return min(n_chunks(), (x_hi + CH - 1u) / CH); }
-    /* out of line: a chunk boundary is crossed once in several batches, and the decode loop has to stay small */
-    __device__ ST_COLD void issue(const u8* g0, u32 from, u32 to, u32 lane) const {
-        if (lane == 0) {
+template <u32 SLOTS, u32 CH, u32 RING_OFF, u32 BAR_OFF, u32 STATE_OFF>
+struct Stream {
+    typedef StWindow Window;
+
+    static __device__ __forceinline__ u32 pack(u32 issued, u32 waited, u32 phase) { return issued | (waited << 12) | (phase << 24); }
+    static __device__ __forceinline__ void wait_upto(u32 a, u32& waited, u32 to, u32& phase) {
 #pragma unroll 1
-            for (u32 c = from; c < to; c++)
-                st_issue(ring_s + (c % SLOTS) * CH, g0 + (size_t)c * CH, min(CH, x_clip - c * CH), bar_s + 8u * (c % SLOTS));
+        for (; waited < to; waited++) {
+            const u32 sl = waited % SLOTS;
+            st_wait(a + BAR_OFF + 8u * sl, (phase >> sl) & 1u);
+            phase ^= 1u << sl;
         }
     }
-    __device__ ST_COLD void wait(u32 from, u32 to) const {
-#pragma unroll 1
-        for (u32 c = from; c < to; c++) st_wait(bar_s + 8u * (c % SLOTS), (c / SLOTS) & 1u);
-    }
-    /* Start a block: the stream is `bytes` long from p (coordinate p & 15); copies end at the last 16-byte boundary
-     * at or below `lim`.  Issues the first chunks and waits for what the first batch reads (up to x_hi).  Returns
-     * x_clip (the caller stores it). */
-    __device__ __forceinline__ u32 open(const u8* p, u32 bytes, const u8* lim, bool on, u32 x_hi, u32 lane) {
+    /* start of a block: the stream is `bytes` long from p; copies end at the last 16-byte boundary at or below lim */
+    static __device__ __forceinline__ void open(u32 a, const u8* p, u32 bytes, const u8* lim, bool on) {
         const u32 x0 = (u32)(reinterpret_cast<uintptr_t>(p) & 15u);
         const u8* g0 = p - x0;
-        x_clip = 0;
-        if (on && lim > g0) {
+        u32 clip = 0;
+        if (on && lim > g0 && bytes >= 64u && bytes < 0xFF0u * CH) { /* 12-bit chunk counters */
             const u64 room = (u64)(lim - g0) & ~15ull;
             const u64 want = ((u64)x0 + bytes + 15ull) & ~15ull;
-            x_clip = (u32)(want < room ? want : room);
+            clip = (u32)(want < room ? want : room);
         }
-        if (x_clip) {
-            if (lane == 0) {
-                for (u32 s = 0; s < SLOTS; s++) st_mbar_reinit(bar_s + 8u * s);
-                st_init_fence();
+        const u32 st = lds32(a + STATE_OFF + 4u);
+        __syncwarp(); /* every lane has read the word before any lane rewrites it */
+        sts32<0>(a + STATE_OFF, clip);
+        sts32<4>(a + STATE_OFF, pack(0u, 0u, st >> 24)); /* the barriers keep their phases from block to block */
+    }
+    /* A batch reads [x_lo, x_hi) (+- slop bytes that aligned word loads may touch): retire the chunks below it, issue
+     * what the ring has room for, wait for what the range needs.  Returns what is resident. */
+    static __device__ __forceinline__ Window need(u32 a, const u8* p, u32 x_lo, u32 x_hi, u32 slop, u32 lane) {
+        Window w;
+        w.ring_s = a + RING_OFF;
+        w.lo = w.hi = 0;
+        const u32 clip = lds32(a + STATE_OFF);
+        if (clip) {
+            const u32 st = lds32(a + STATE_OFF + 4u);
+            __syncwarp(); /* every lane has read the word before any lane rewrites it */
+            u32 issued = st & 0xFFFu, waited = (st >> 12) & 0xFFFu, phase = st >> 24;
+            const u32 n = (clip + CH - 1u) / CH;
+            const u32 first = min(n, (x_lo >= slop ? x_lo - slop : 0u) / CH); /* chunks below it are dead */
+            wait_upto(a, waited, min(issued, first), phase);                 /* ... but land before their slot is reused */
+            if (issued < first) issued = waited = first;                     /* never asked for (a giant run): skipped */
+            const u32 may = min(n, first + SLOTS);
+            if (issued < may) {
+                if (lane == 0) {
+                    const u8* g0 = p - (reinterpret_cast<uintptr_t>(p) & 15u);
+#pragma unroll 1
+                    for (u32 c = issued; c < may; c++)
+                        st_issue(a + RING_OFF + (c % SLOTS) * CH, g0 + (size_t)c * CH, min(CH, clip - c * CH),
+                                 a + BAR_OFF + 8u * (c % SLOTS));
+                }
+                issued = may;
             }
+            wait_upto(a, waited, min(issued, (x_hi + slop + CH - 1u) / CH), phase);
+            sts32<4>(a + STATE_OFF, pack(issued, waited, phase));
+            w.lo = first * CH;
+            w.hi = min(waited * CH, clip);
+        }
+        return w;
+    }
+    /* end of a block, early or not: nothing stays in flight */
+    static __device__ __forceinline__ void close(u32 a) {
+        if (lds32(a + STATE_OFF)) {
+            const u32 st = lds32(a + STATE_OFF + 4u);
             __syncwarp();
-            issue(g0, 0, issued_at(x0), lane);
-            wait(0, waited_at(x_hi));
-        }
-        return x_clip;
-    }
-    /* from a batch at [lo, hi) to the next one at [nlo, nhi) */
-    __device__ __forceinline__ void step(const u8* p, u32 lo, u32 hi, u32 nlo, u32 nhi, u32 lane) const {
-        if (x_clip) {
-            const u32 a = issued_at(lo), b = issued_at(nlo);
-            if (a < b) issue(p - (reinterpret_cast<uintptr_t>(p) & 15u), a, b, lane);
-            const u32 c = waited_at(hi), d = waited_at(nhi);
-            if (c < d) wait(c, d);
+            u32 issued = st & 0xFFFu, waited = (st >> 12) & 0xFFFu, phase = st >> 24;
+            wait_upto(a, waited, issued, phase);
+            sts32<4>(a + STATE_OFF, pack(issued, waited, phase));
         }
     }
-    /* the block ends inside the batch at [lo, hi): nothing may stay in flight */
-    __device__ __forceinline__ void close(u32 lo, u32 hi) const {
-        if (x_clip) wait(waited_at(hi), issued_at(lo));
-    }
-    __device__ __forceinline__ bool staged(u32 x_hi) const { return x_hi <= x_clip; }
 };
 
-typedef StageStream<ST_SLOTS, ST_CH> SeqStream;
-typedef StageStream<ST_LIT_SLOTS, ST_LIT_CH> LitStream;
 /* layout of a warp's staging area at shared address a: token ring, offset ring, [literal ring,] mbarriers, state */
+#define ST_OFF_LIT (2u * ST_RING)
 #define ST_OFF_BAR (2u * ST_RING + (ZXC_STAGE_LIT ? ST_LIT_RING : 0u))
 #define ST_OFF_STATE (ST_OFF_BAR + ST_BAR_BYTES)
-__device__ __forceinline__ SeqStream st_tok(u32 a) {
-    SeqStream s;
-    s.ring_s = a;
-    s.bar_s = a + ST_OFF_BAR;
-    s.x_clip = lds32(a + ST_OFF_STATE);
-    return s;
-}
-__device__ __forceinline__ SeqStream st_off(u32 a) {
-    SeqStream s;
-    s.ring_s = a + ST_RING;
-    s.bar_s = a + ST_OFF_BAR + 8u * ST_SLOTS;
-    s.x_clip = lds32(a + ST_OFF_STATE + 4u);
-    return s;
-}
-__device__ __forceinline__ LitStream st_lit(u32 a) {
-    LitStream s;
-    s.ring_s = a + 2u * ST_RING;
-    s.bar_s = a + ST_OFF_BAR + 16u * ST_SLOTS;
-    s.x_clip = lds32(a + ST_OFF_STATE + 8u);
-    return s;
-}
+typedef Stream<ST_SLOTS, ST_CH, 0u, ST_OFF_BAR, ST_OFF_STATE> TokStream;
+typedef Stream<ST_SLOTS, ST_CH, ST_RING, ST_OFF_BAR + 8u * ST_SLOTS, ST_OFF_STATE + 8u> OffStream;
+typedef Stream<ST_LIT_SLOTS, ST_LIT_CH, ST_OFF_LIT, ST_OFF_BAR + 16u * ST_SLOTS, ST_OFF_STATE + 16u> LitStream;
+
 /* once per warp, before its first block */
 __device__ __forceinline__ void st_init(u32 a, u32 lane) {
     if (lane == 0) {
@@ -255,84 +249,8 @@ __device__ __forceinline__ void st_init(u32 a, u32 lane) {
     __syncwarp();
 }
 
-#if ZXC_STAGE_LIT
-/* The literal stream.  Its cursor moves by the batch's literal total -- anything from nothing to the whole block (a
- * giant run skips the ring altogether) -- so its counters are kept, packed into one shared word: chunks issued (12
- * bits), chunks waited for (12 bits), the parity the next wait on each of the four slots asks for (4 bits).  A lane's
- * literal run comes out of the ring when it lies, with the 8 bytes either side that the aligned word loads of the
- * copy helpers may touch, inside the resident chunks and does not wrap the ring; otherwise out of global memory. */
-struct LitWindow {
-    u32 ring_s;
-    u32 lo, hi; /* coordinates [lo, hi) are resident */
-};
-__device__ __forceinline__ u32 lit_pack(u32 issued, u32 waited, u32 phase) { return issued | (waited << 12) | (phase << 24); }
-__device__ __forceinline__ void lit_wait(const LitStream& s, u32& waited, u32 to, u32& phase) {
-    for (; waited < to; waited++) {
-        const u32 sl = waited % ST_LIT_SLOTS;
-        st_wait(s.bar_s + 8u * sl, (phase >> sl) & 1u);
-        phase ^= 1u << sl;
-    }
-}
-/* start of a block */
-__device__ __forceinline__ void lit_open(u32 a, const u8* p, u32 bytes, const u8* lim, bool on) {
-    const u32 x0 = (u32)(reinterpret_cast<uintptr_t>(p) & 15u);
-    const u8* g0 = p - x0;
-    u32 clip = 0;
-    if (on && lim > g0 && bytes >= 64u && bytes < 0x1FE000u) { /* 12-bit chunk counters */
-        const u64 room = (u64)(lim - g0) & ~15ull;
-        const u64 want = ((u64)x0 + bytes + 15ull) & ~15ull;
-        clip = (u32)(want < room ? want : room);
-    }
-    sts32<8>(a + ST_OFF_STATE, clip);
-    const u32 st = lds32(a + ST_OFF_STATE + 12u);
-    __syncwarp(); /* every lane has read the word before any lane rewrites it */
-    sts32<12>(a + ST_OFF_STATE, lit_pack(0u, 0u, st >> 24)); /* the barriers keep their phases from block to block */
-}
-/* a batch reads literals [x_lo, x_hi): bring the ring up to date, say what is resident */
-__device__ __forceinline__ LitWindow lit_need(u32 a, const u8* p, u32 x_lo, u32 x_hi, u32 lane) {
-    const LitStream s = st_lit(a);
-    LitWindow w;
-    w.ring_s = s.ring_s;
-    w.lo = w.hi = 0;
-    if (s.x_clip) {
-        const u32 st = lds32(a + ST_OFF_STATE + 12u);
-        __syncwarp(); /* every lane has read the word before any lane rewrites it */
-        u32 issued = st & 0xFFFu, waited = (st >> 12) & 0xFFFu, phase = st >> 24;
-        const u32 n = s.n_chunks();
-        const u32 first = min(n, (x_lo >= 8u ? x_lo - 8u : 0u) / ST_LIT_CH); /* chunks below it are dead */
-        lit_wait(s, waited, min(issued, first), phase);                      /* ... but land before their slot is reused */
-        if (issued < first) issued = waited = first;                         /* never asked for: skipped */
-        const u32 may = min(n, first + ST_LIT_SLOTS);
-        if (issued < may) {
-            if (lane == 0) {
-                const u8* g0 = p - (reinterpret_cast<uintptr_t>(p) & 15u);
-                for (u32 c = issued; c < may; c++)
-                    st_issue(s.ring_s + (c % ST_LIT_SLOTS) * ST_LIT_CH, g0 + (size_t)c * ST_LIT_CH,
-                             min(ST_LIT_CH, s.x_clip - c * ST_LIT_CH), s.bar_s + 8u * (c % ST_LIT_SLOTS));
-            }
-            issued = may;
-        }
-        lit_wait(s, waited, min(issued, (x_hi + 8u + ST_LIT_CH - 1u) / ST_LIT_CH), phase);
-        sts32<12>(a + ST_OFF_STATE, lit_pack(issued, waited, phase));
-        w.lo = first * ST_LIT_CH;
-        w.hi = min(waited * ST_LIT_CH, s.x_clip);
-    }
-    return w;
-}
-/* end of a block, early or not: nothing stays in flight */
-__device__ __forceinline__ void lit_close(u32 a) {
-    const LitStream s = st_lit(a);
-    if (s.x_clip) {
-        const u32 st = lds32(a + ST_OFF_STATE + 12u);
-        __syncwarp();
-        u32 issued = st & 0xFFFu, waited = (st >> 12) & 0xFFFu, phase = st >> 24;
-        lit_wait(s, waited, issued, phase);
-        sts32<12>(a + ST_OFF_STATE, lit_pack(issued, waited, phase));
-    }
-}
 /* generic pointer of the literal at coordinate x when [x - 8, x + n + 8) is resident and does not wrap; else 0 */
-__device__ __forceinline__ const u8* lit_ptr(const LitWindow& w, u32 x, u32 n) {
+__device__ __forceinline__ const u8* lit_ptr(const StWindow& w, u32 x, u32 n) {
     const bool in = x >= w.lo + 8u && x + n + 8u <= w.hi && ((x - 8u) / ST_LIT_RING) == ((x + n + 7u) / ST_LIT_RING);
     return in ? st_generic(w.ring_s + (x & (ST_LIT_RING - 1u))) : (const u8*)0;
 }
-#endif

@@ -4,11 +4,11 @@
  * copies, launches.
  *
  * Decode launches (launch_decode below):
- *   zxc_decode2_kernel  (zxc_decode2.cuh) one CTA per block of <= 64 KiB, window in shared memory,
- *                       cp.async.bulk in and out; takes GLO / GHI blocks with raw sections and RAW blocks
- *   zxc_decode_kernel   (zxc_decode.cuh)  one warp per block, any block size / section encoding;
- *                       runs second over whatever the first kernel deferred, or alone for block
- *                       sizes above 64 KiB and for checksum-verifying decodes
+ *   zxc_decode_kernel   (zxc_decode.cuh)  one warp per block, any block size / section encoding: every launch by
+ *                       default (instances: sequence-centric or output-centric body, with / without dictionary)
+ *   zxc_decode2_kernel  (zxc_decode2.cuh) one CTA per block of <= 64 KiB, window in shared memory, cp.async.bulk in
+ *                       and out; only with ZXC_B200_DECODE_V2=1 (it measured 10x slower); what
+ *                       it defers (entropy-coded sections, checksum verification) goes to zxc_decode_kernel
  * Encode: zxc_encode.cuh (levels 1-5), zxc_encode_opt.cuh (levels 6-7).
  */
 #include <cuda_runtime.h>
@@ -748,9 +748,18 @@ static int launch_decode(const void* d_src, void* d_dst, const zxc_b200_job_t* d
         P.flags |= FLAG_DEFERRED;
         P.counter = d_counter + 1;
     }
-    if (P.flags & FLAG_DEFERRED) zxc_decode_kernel<false, true><<<grid, CTA_THREADS, DECODE_SMEM_BYTES, st>>>(P);
-    else if (units) zxc_decode_kernel<true, false><<<grid, CTA_THREADS, DECODE_SMEM_BYTES, st>>>(P);
-    else zxc_decode_kernel<false, false><<<grid, CTA_THREADS, DECODE_SMEM_BYTES, st>>>(P);
+    /* the dictionary-free instance carries neither the dictionary pointer nor its source classification (zxc_decode.cuh) */
+    const bool has_dict = P.dict != NULL && P.dict_size != 0;
+    if (P.flags & FLAG_DEFERRED) {
+        if (has_dict) zxc_decode_kernel<false, true, true><<<grid, CTA_THREADS, DECODE_SMEM_BYTES, st>>>(P);
+        else zxc_decode_kernel<false, true, false><<<grid, CTA_THREADS, DECODE_SMEM_BYTES, st>>>(P);
+    } else if (units) {
+        if (has_dict) zxc_decode_kernel<true, false, true><<<grid, CTA_THREADS, DECODE_SMEM_BYTES, st>>>(P);
+        else zxc_decode_kernel<true, false, false><<<grid, CTA_THREADS, DECODE_SMEM_BYTES, st>>>(P);
+    } else {
+        if (has_dict) zxc_decode_kernel<false, false, true><<<grid, CTA_THREADS, DECODE_SMEM_BYTES, st>>>(P);
+        else zxc_decode_kernel<false, false, false><<<grid, CTA_THREADS, DECODE_SMEM_BYTES, st>>>(P);
+    }
     __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
     return cudaGetLastError() == cudaSuccess ? ZXC_OK : ZXC_B200_ERROR_CUDA;
 }
