@@ -32,3 +32,13 @@ EXPORT uint32_t zxhh_estimate_lit_bits(const uint32_t* hist, uint32_t sampled) {
     return r;
 }
 EXPORT uint64_t zxhh_work_bytes(void) { return sizeof(zxh_work_t); }
+
+/* zxh_cost_add on its own: bits and work of c items of level lc (group size 2^g) from index `at`, masses pf[first..] */
+EXPORT void zxhh_cost_add(int lc, int g, uint32_t at, uint32_t c, const uint64_t* pf, uint32_t first, uint64_t* bits,
+                          uint64_t* work) {
+    zxh_cost_t acc;
+    acc.bits = acc.work = 0;
+    zxh_cost_add(&acc, lc, g, at, c, pf, first);
+    *bits = acc.bits;
+    *work = acc.work;
+}

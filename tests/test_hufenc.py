@@ -164,3 +164,44 @@ def test_package_merge_wide_sweep(libs):
             ra = h.zxhh_build_code_lengths(f.ctypes.data, a.ctypes.data, cap)
             rb = r.zxri_build_code_lengths(f.ctypes.data, b.ctypes.data, cap)
             assert ra == rb and np.array_equal(a, b), (t, cap, n_sym, kind)
+
+
+def test_block_decomposition_matches_left_to_right_greedy(libs):
+    """zxh_cost_add splits an index interval into maximal aligned power-of-two blocks from its two ends; the plain
+    statement of the same split (zxc_huffman.c:343-431 walks it left to right: at x take the largest aligned block
+    that fits) must give the same sums for every interval of a 2^7 code space, grouped or not."""
+    h, _ = libs
+    h.zxhh_cost_add.restype = None
+    h.zxhh_cost_add.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(5)
+    mass = rng.integers(1, 1000, 300).astype(np.uint64)
+    pf = np.concatenate([[0], np.cumsum(mass)]).astype(np.uint64)
+
+    def weight(length, d):
+        return length + 1 - d + (24 if d > 6 else 0)
+
+    def greedy(lc, g, at, c, first):
+        bits = (lc + g) * int(pf[first + c] - pf[first])
+        work, x, i, end = 0, at, first, at + c
+        while x < end:
+            low = (x & -x) if x else 1 << 30
+            fit = 1 << ((end - x).bit_length() - 1)
+            sz = min(low, fit)
+            work += int(pf[i + sz] - pf[i]) * weight(lc + g, (sz.bit_length() - 1) + g)
+            x += sz
+            i += sz
+        return bits, work
+
+    bits, work = C.c_uint64(), C.c_uint64()
+    checked = 0
+    for lc, g in ((7, 0), (5, 2), (6, 1), (3, 0)):
+        n = 1 << lc
+        for at in range(0, n):
+            for c in range(0, n - at + 1):
+                first = int(rng.integers(0, 300 - c)) if c < 300 else 0
+                if first + c > 300:
+                    continue
+                h.zxhh_cost_add(lc, g, at, c, pf.ctypes.data, first, C.byref(bits), C.byref(work))
+                assert (bits.value, work.value) == greedy(lc, g, at, c, first), (lc, g, at, c)
+                checked += 1
+    assert checked > 10000

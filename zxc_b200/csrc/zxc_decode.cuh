@@ -34,6 +34,23 @@ typedef uint64_t u64;
 typedef int32_t i32;
 
 #define FULL 0xFFFFFFFFu
+#ifndef ZXC_FASTMOD
+#define ZXC_FASTMOD 0
+#endif
+#ifndef ZXC_TAIL_SMEM
+#define ZXC_TAIL_SMEM 0
+#endif
+#ifndef ZXC_ALIGNED_LD
+#define ZXC_ALIGNED_LD 0
+#endif
+#ifndef ZXC_HINTS
+#define ZXC_HINTS 0
+#endif
+#if ZXC_HINTS
+#define ZXC_RARE(x) __builtin_expect(!!(x), 0)
+#else
+#define ZXC_RARE(x) (x)
+#endif
 #ifndef ZXC_STAT
 #define ZXC_STAT(i, v) /* tests/simt counts events here (lane 0 only); nothing in the product build */
 #endif
@@ -481,8 +498,19 @@ __device__ __forceinline__ void warp_match_to_ring(const Window& w, u32 d, u32 o
         /* period-`off` replication of the complete window [d-off, d): lane r holds window byte r, byte k of the match
          * is window byte k mod off -- fetched by shuffle, the residue stepped by 32 mod off (no division per byte) */
         const u32 mine = lane < off ? (u32)window_byte(w, (i32)d - (i32)off + (i32)lane) : 0u;
+#if ZXC_FASTMOD
+        /* x mod off for x <= 32, off < 32 without the integer division: with a reciprocal good to a few ulp the float
+         * quotient is at most one too small at exact multiples and never too large (between multiples the true quotient
+         * keeps a margin of 1 / off from the next integer), so one subtraction repairs it */
+        const float inv = __fdividef(1.0f, (float)off);
+        u32 step = 32u - (u32)(32.0f * inv) * off;
+        if (step >= off) step -= off;
+        u32 r = lane - (u32)((float)lane * inv) * off;
+        if (r >= off) r -= off;
+#else
         const u32 step = 32u % off;
         u32 r = lane % off;
+#endif
         for (u32 c = 0; c < n; c += 32) {
             const u32 b = __shfl_sync(FULL, mine, r);
             if (c + lane < n) w.ring[(d + c + lane) & mask] = (u8)b;
@@ -797,9 +825,19 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, u8* out, u32 cap, const 
 #else
             if (!ghi) {
                 a = tok[i];
+#if ZXC_ALIGNED_LD
+                if (enc_off) b = (u32)offs[i];
+                else if (reinterpret_cast<uintptr_t>(offs) & 1u) b = ld16(offs + 2 * (size_t)i);
+                else b = (u32)reinterpret_cast<const unsigned short*>(offs)[i];
+#else
                 b = enc_off ? (u32)offs[i] : ld16(offs + 2 * (size_t)i);
+#endif
             } else {
+#if ZXC_ALIGNED_LD
+                a = (reinterpret_cast<uintptr_t>(tok) & 3u) ? ld32(tok + 4 * (size_t)i) : reinterpret_cast<const u32*>(tok)[i];
+#else
                 a = ld32(tok + 4 * (size_t)i);
+#endif
             }
 #endif
             if (!ghi) {
@@ -823,7 +861,7 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, u8* out, u32 cap, const 
                 k++;
             }
             if (e_ml) ml += k < n_val ? vals[k] : 0u;
-        } else if (m_ll | m_ml) {
+        } else if (ZXC_RARE((m_ll | m_ml) != 0)) {
             const u32 ord_ll = __popc(m_ll & lt_mask) + __popc(m_ml & lt_mask);
             k_esc = __popc(m_ll) + __popc(m_ml);
             u32 my_pos = ext_end; /* cursor where this lane's first varint starts */
@@ -847,7 +885,7 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, u8* out, u32 cap, const 
         const u32 out_start = O + s_tot - tot;
         const u32 mdst = out_start + ll;
 
-        if (m == 0) {
+        if (ZXC_RARE(m == 0)) {
             /* ---- giant sequence (lane 0): bypass the ring, global -> global ---- */
             const u32 g_ll = __shfl_sync(FULL, ll, 0), g_ml = __shfl_sync(FULL, ml, 0),
                       g_off = __shfl_sync(FULL, off, 0);
@@ -887,7 +925,7 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, u8* out, u32 cap, const 
         const bool ovf = act && (lit_start + ll > n_lit_avail || out_start + tot > cap);
         const bool bad = act && (mdst + dict_size < off);
         const u32 m_err = __ballot_sync(FULL, ovf || bad);
-        if (m_err) {
+        if (ZXC_RARE(m_err != 0)) {
             const int code = ovf ? ZXC_ERROR_OVERFLOW : ZXC_ERROR_BAD_OFFSET;
             ST_CLOSE();
             return __shfl_sync(FULL, code, __ffs(m_err) - 1);
@@ -973,7 +1011,7 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, u8* out, u32 cap, const 
             ZXC_STAT(7, __ballot_sync(FULL, ready && lok) != 0);      /* passes with a per-lane item */
             if (m_grp) balanced_copy_words(ring_s, m_grp, it_d, it_sp, it_n, lane);
             u32 m_slow = __ballot_sync(FULL, ready && !lok && !gok);
-            while (m_slow) { /* ring wrap, close overlap, dictionary, straddling sources: byte paths */
+            while (ZXC_RARE(m_slow != 0)) { /* ring wrap, close overlap, dictionary, straddling sources: byte paths */
                 const int j = __ffs(m_slow) - 1;
                 m_slow &= m_slow - 1;
                 const u32 d = __shfl_sync(FULL, it_d, j), n = __shfl_sync(FULL, it_n, j);
@@ -999,7 +1037,11 @@ __device__ int decode_lz_block(const u8* pay, u32 comp, u8* out, u32 cap, const 
                 const u32 n = pk & 0x7FFFFFFFu;
                 if (pk >> 31) { /* the whole source is in the ring and the match does not overlap itself */
                     const u32 sl = __shfl_sync(FULL, (u32)src_lo, j);
+#if ZXC_TAIL_SMEM
+                    for (u32 k = lane; k < n; k += 32) sts8<0>(ring_s + ((d + k) & mask), lds8(ring_s + ((sl + k) & mask)));
+#else
                     for (u32 k = lane; k < n; k += 32) ring[(d + k) & mask] = ring[(sl + k) & mask];
+#endif
                 } else {
                     warp_match_to_ring(w, d, __shfl_sync(FULL, off, j), n, lane);
                 }
