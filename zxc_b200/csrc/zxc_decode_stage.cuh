@@ -32,9 +32,6 @@
 #ifndef ZXC_BULK_FLUSH
 #define ZXC_BULK_FLUSH 0 /* the ring leaves the SM by cp.async.bulk shared -> global instead of LDS.128 / STG.128 */
 #endif
-#ifndef ST_COLD
-#define ST_COLD __forceinline__ /* __noinline__ measured: a call inside the decode loop costs far more than its size */
-#endif
 #define ST_SLOTS 2u
 #define ST_CH 256u                       /* token / offset chunk: 8 GLO batches of tokens, 4 of offsets, 2 GHI batches */
 #define ST_RING (ST_SLOTS * ST_CH)
@@ -51,10 +48,6 @@
 
 #ifdef __CUDACC__
 __device__ __forceinline__ void st_mbar_init(u32 bar) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void st_mbar_reinit(u32 bar) {
-    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void st_init_fence() {
@@ -112,10 +105,6 @@ extern u32 simt_bar_base;
 void simt_stage_fail(const char* what);
 static inline u32 simt_bar_idx(u32 bar) { return ((bar - simt_bar_base) / 8u) & 63u; }
 static inline void st_mbar_init(u32 bar) { simt_bar_issued[simt_bar_idx(bar)] = simt_bar_waited[simt_bar_idx(bar)] = 0; }
-static inline void st_mbar_reinit(u32 bar) {
-    if (simt_bar_issued[simt_bar_idx(bar)] != simt_bar_waited[simt_bar_idx(bar)]) simt_stage_fail("re-init of a barrier with a copy in flight");
-    st_mbar_init(bar);
-}
 static inline void st_init_fence() {}
 static inline void st_issue(u32 sdst, const u8* gsrc, u32 bytes, u32 bar) {
     const u32 b = simt_bar_idx(bar);
