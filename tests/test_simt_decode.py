@@ -94,6 +94,17 @@ def test_kernel_source_damaged_blocks_fail_like_the_reference(prod, ref):
         assert checked >= 40
 
 
+def test_kernel_source_differential_fuzz_smoke():
+    """a short fixed-seed run of the open-ended emulator fuzz tools (tests/simt_fuzz.py, tests/simt_fuzz_dict.py)"""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    for tool, secs in (("simt_fuzz.py", "12"), ("simt_fuzz_dict.py", "8")):
+        r = subprocess.run([sys.executable, os.path.join(here, tool), "1", secs], stdout=subprocess.PIPE,
+                           stderr=subprocess.STDOUT, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-1500:]
+
+
 @pytest.mark.skipif(bool(os.environ.get("ZXC_SIMT_SO")), reason="already running a variant build")
 def test_kernel_source_with_bulk_copy_staging():
     """The opt-in TMA flavour of the kernel (token / offset / literal sections staged through shared memory by
